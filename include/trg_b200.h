@@ -1,0 +1,137 @@
+/* trg_b200.h -- C ABI of the B200-native (sm_100a) hetero-SAGE hot path.
+ *
+ * The reference (ramkp990/Truth_Recommendation_GNN) is pure Python and has no FFI layer; its
+ * seam is the PyG operator API used by the scripts.  Each entry point below names the
+ * reference lines it replaces.  The Python binding a maintainer adds is in INTEGRATION.md; the
+ * host-side mirror of the reference interface lives in truth_recommendation_gnn_b200/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
+ *  - int return: 0 = ok, non-zero = TRG_E_*; trg_last_error() returns a thread-local message;
+ *  - no ownership transfer: all buffers including workspaces are allocated by the caller;
+ *  - stateless, asynchronous on the given stream (a cudaStream_t passed as void*), no host
+ *    synchronisation inside, re-entrant across streams and threads;
+ *  - dtype: TRG_F32 (fp32 storage) or TRG_BF16 (bf16 storage, fp32 accumulation);
+ *  - row widths (F, H) must make a row a multiple of 16 bytes (F % 4 == 0 for fp32,
+ *    F % 8 == 0 for bf16) and tables must be 16-byte aligned;
+ *  - edge counts must be < 2^31 per relation; node ids are stored as int32 in the CSR.
+ */
+#ifndef TRG_B200_H
+#define TRG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRG_ABI_VERSION 1
+
+enum { TRG_F32 = 0, TRG_BF16 = 1 };
+enum {
+  TRG_OK = 0,
+  TRG_E_ARG = 1,        /* bad argument (null pointer, unsupported width, size overflow) */
+  TRG_E_WORKSPACE = 2,  /* workspace too small */
+  TRG_E_CUDA = 3,       /* a CUDA runtime call failed (message has the CUDA error string) */
+  TRG_E_UNSUPPORTED = 4
+};
+
+/* ---- library ---------------------------------------------------------------------------- */
+int trg_abi_version(void);
+const char* trg_last_error(void);
+/* Number of kernels this library has launched in the calling process (all threads). */
+int64_t trg_launch_count(void);
+
+/* ---- A0 / K0: destination-sorted CSR ---------------------------------------------------------
+ * Replaces the implicit COO->dense scatter PyG performs on the reference's edge_index tensors
+ * (build_graph.py:387,394,402; local ids train_gnn.py:128-133; .flip(0) train_gnn.py:142).
+ * Stable LSD radix sort by key: bit-exact with
+ *     perm = argsort(key, stable); rowptr = [0, cumsum(bincount(key, N))]; col = other[perm]; eid = perm
+ * Call with (other = src, key = dst) for the forward CSR and (other = dst, key = src) for the
+ * transposed one.  Keys must lie in [0, n_key) (the caller validates).  col / eid may be NULL. */
+size_t trg_csr_workspace_bytes(int64_t n_edges, int64_t n_key);
+int trg_csr_build(const int64_t* other, const int64_t* key, int64_t n_edges, int64_t n_key,
+                  int32_t* rowptr /* [n_key+1] */, int32_t* col /* [E] */, int32_t* eid /* [E] */,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- A1+A2 / K1: fused gather + segmented mean (SAGEConv propagate + MeanAggregation) ------------
+ * Replaces x_j = x_src.index_select(0, src); scatter(x_j, dst, reduce='mean') inside the
+ * SAGEConv calls at train_gnn.py:177-184,194-197.  mean[r] = (sum_{j in row r} x_src[col[j]]) /
+ * max(deg r, 1), neighbours added in CSR order (== edge order), so fp32 results equal the CPU
+ * scatter_add_ bit for bit.  inv_deg_out (nullable) receives 1 / max(deg, 1). */
+int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_src,
+                     int64_t n_dst, int32_t feat, int dtype,
+                     void* mean_out /* [n_dst, feat] dtype */, float* inv_deg_out /* [n_dst] */,
+                     void* stream);
+
+/* ---- A7 / K2: atomic-free backward of K1 w.r.t. the sources (layers >= 2) ----------------------
+ * Replaces autograd of index_select + scatter-mean (index_add / gather).  Uses the transposed
+ * CSR (rows = sources, col_t = destination of each edge):
+ *     g_src[s] = sum_{j in row s} g_mean[col_t[j]] * inv_deg[col_t[j]]      (inv_deg nullable) */
+int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
+                     const void* g_mean, int64_t n_src, int32_t feat, int dtype,
+                     void* g_src_out /* [n_src, feat] dtype */, void* stream);
+
+/* ---- generic weighted segmented gather-sum (used by the loss backward) ------------------------
+ *     out[r] (+)= scale * sum_{j in row r} coef[eid[j]] * x[col[j]]
+ * scale is a device scalar (nullable = 1); accumulate != 0 adds to out. */
+int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                    const float* coef, const float* scale, const void* x,
+                    int64_t n_rows, int32_t feat, int dtype, void* out, int accumulate,
+                    void* stream);
+
+/* ---- A5+A6 / K4: fused positive/negative edge score + BCE-with-logits -------------------------
+ * Replaces train_gnn.py:259-281:  pos = <u[pos_u], p[pos_p]>, neg = <u[pos_u], p[neg_p]>,
+ *     loss = wbar * mean(softplus(-pos)) + mean(softplus(neg)),   wbar = mean(w[pos_p + U])
+ * (the reference's BCEWithLogitsLoss is a scalar mean, so its "weighted" loss is exactly this).
+ * Positive edges are given grouped by user: rowptr_u/col_p/eid = trg_csr_build(other = pos_p,
+ * key = pos_u).  neg_p is in ORIGINAL edge order (index it with eid).
+ * Outputs: loss_out[1]; and when c_pos/c_neg/g_u are non-NULL the backward ingredients
+ *     c_pos[e] = dloss/dpos_e,  c_neg[e] = dloss/dneg_e   (original edge order)
+ *     g_u[r]   = sum_e c_pos[e] p[pos_p[e]] + c_neg[e] p[neg_p[e]]   (dloss/du, dtype rows)
+ * dloss/dp is then two trg_gather_wsum calls over the post-grouped structures. */
+size_t trg_edge_bce_workspace_bytes(int64_t n_users);
+int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, const int32_t* eid,
+                     const int64_t* neg_p, const void* u, const void* p,
+                     int64_t n_users, int64_t n_edges, int32_t hidden, int dtype,
+                     const float* wbar /* device scalar */, float* loss_out,
+                     float* c_pos, float* c_neg, void* g_u,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- A3+A4 / K3: SAGE projections + relation combine + ReLU ---------------------------------
+ * Replaces lin_l(mean) + lin_r(x_dst) of every SAGEConv and the combine of
+ * train_gnn.py:187-198.  out = act( sum_i alpha_i * ( A_i[n, k_i] @ W_i[h, k_i]^T ) + bias ),
+ * up to 4 (A, W) pairs (user rows: mean_direct, x, mean_social, x; post rows: mean, x).
+ * fp32 inputs are multiplied as 3xTF32 split products on tcgen05 (fp32-accurate), bf16 inputs as
+ * kind::f16 with fp32 TMEM accumulation. */
+typedef struct {
+  const void* a;      /* [n_rows, k] dtype, row-major, 16B-aligned */
+  const void* w;      /* [hidden, k] dtype, row-major (torch Linear.weight layout) */
+  int32_t k;
+  float alpha;
+} trg_proj_term;
+int trg_sage_proj_fwd(const trg_proj_term* terms /* host */, int32_t n_terms,
+                      const float* bias /* [hidden] fp32, nullable; already alpha-combined */,
+                      int64_t n_rows, int32_t hidden, int dtype, int relu,
+                      void* out /* [n_rows, hidden] dtype */, void* stream);
+
+/* ---- A9+A10 / K5: score contraction + top-k ---------------------------------------------------
+ * Replaces scores = torch.mm(user_emb, known_post_emb.T); torch.topk(scores, min(K, n))
+ * (inference.py:427-428; train_gnn.py:335-341).  Never materialises the score matrix.  Total
+ * order: score descending, id ascending.  ids_out are global: local + id_offset (shards).
+ * k_out = min(k, n_cat) columns are written; rows are q rows. */
+size_t trg_score_topk_workspace_bytes(int64_t n_query, int64_t n_cat, int32_t hidden, int32_t k);
+int trg_score_topk(const void* q /* [B, H] */, const void* cat /* [P, H] */,
+                   int64_t n_query, int64_t n_cat, int32_t hidden, int dtype, int32_t k,
+                   int64_t id_offset, float* vals_out /* [B, k_out] */, int64_t* ids_out /* [B, k_out] */,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* Merge n_lists per-row sorted (vals, ids) lists of length k_in into the top k_out. */
+int trg_topk_merge(const float* vals_in /* [B, n_lists*k_in] */, const int64_t* ids_in,
+                   int64_t n_query, int32_t n_lists, int32_t k_in, int32_t k_out,
+                   float* vals_out, int64_t* ids_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRG_B200_H */

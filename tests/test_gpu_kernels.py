@@ -1,0 +1,260 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the CPU oracle on the same
+seeded inputs.  Bit-exact for integer / index work and for the fp32 CSR-order mean; 1e-5
+relative for other fp32 results; 1e-2 for bf16 storage (fp32 accumulate)."""
+import pytest
+import torch
+
+import truth_recommendation_gnn_b200 as trg
+from oracle import cint
+from oracle import csr as ocsr
+from oracle import sage as osage
+from oracle import topk as otopk
+from tests.util import TOL_BF16, TOL_F32, assert_close
+from truth_recommendation_gnn_b200 import functional as Fn
+from truth_recommendation_gnn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------- K0
+@pytest.mark.parametrize("n_src,n_dst,e,skew", [
+    (50, 70, 600, False), (1000, 3000, 50_000, False), (300, 200, 40_000, True),
+    (5, 1, 1000, False),            # a single destination: one very long row
+    (70_000, 300_000, 400_000, False),  # 3 radix passes (19 bits), many empty rows
+    (4, 4, 0, False),               # E = 0
+    (0, 3, 0, False),               # N_src = 0 (inference.py:412-419)
+    (10, 257, 5000, False),         # 2 passes, second one nearly empty
+])
+def test_csr_build_bit_exact(dev, n_src, n_dst, e, skew):
+    g = torch.Generator().manual_seed(e + n_dst)
+    src = torch.randint(0, max(n_src, 1), (e,), generator=g)
+    if skew:
+        dst = (n_dst * torch.rand(e, generator=g, dtype=torch.float64).pow(3)).long().clamp_(0, n_dst - 1)
+    else:
+        dst = torch.randint(0, max(n_dst, 1), (e,), generator=g)
+    ei = torch.stack([src, dst])
+    rp, col, eid = ocsr.csr_by_dst(ei, n_dst)
+    c = trg.build_csr(ei[0].to(dev), ei[1].to(dev), n_dst, n_src)
+    assert torch.equal(c.rowptr.cpu().long(), rp)
+    assert torch.equal(c.eid.cpu().long(), eid)
+    assert torch.equal(c.col.cpu().long(), col)
+    if e:
+        rp2, col2, eid2 = cint.csr_by_dst(ei, n_dst)   # plain-C oracle agrees too
+        assert torch.equal(c.eid.cpu().long(), eid2) and torch.equal(c.rowptr.cpu().long(), rp2)
+    # transpose = same routine with roles swapped
+    rpt, colt, eidt = ocsr.csr_by_src(ei, n_src)
+    ct = trg.build_csr(ei[1].to(dev), ei[0].to(dev), n_src, n_dst)
+    assert torch.equal(ct.rowptr.cpu().long(), rpt) and torch.equal(ct.col.cpu().long(), colt)
+    assert torch.equal(ct.eid.cpu().long(), eidt)
+
+
+def test_csr_build_rejects_out_of_range(dev):
+    ei = torch.tensor([[0, 1], [0, 5]], device=dev)
+    with pytest.raises(IndexError):
+        trg.build_csr(ei[0], ei[1], 3, 2)
+
+
+def test_csr_is_deterministic(dev):
+    g = synth.synth_graph(2000, 5000, 60_000, 10_000, 8, seed=9, skew=True).to(dev)
+    ei = g.edge_index_dict[synth.REL_ENGAGE]
+    a = trg.build_csr(ei[0], ei[1], 5000, 2000)
+    b = trg.build_csr(ei[0], ei[1], 5000, 2000)
+    assert torch.equal(a.eid, b.eid) and torch.equal(a.col, b.col) and torch.equal(a.rowptr, b.rowptr)
+
+
+# ---------------------------------------------------------------------------------------- K1
+def _agg_case(n_src, n_dst, e, f, seed, skew=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_src, f, generator=g)
+    src = torch.randint(0, max(n_src, 1), (e,), generator=g)
+    if skew:
+        dst = (n_dst * torch.rand(e, generator=g, dtype=torch.float64).pow(3)).long().clamp_(0, n_dst - 1)
+    else:
+        dst = torch.randint(0, max(n_dst, 1), (e,), generator=g)
+    return x, torch.stack([src, dst])
+
+
+@pytest.mark.parametrize("f", [4, 8, 16, 32, 64, 96, 128, 256, 512])
+def test_agg_fwd_fp32_bit_exact(dev, f):
+    torch.set_num_threads(1)
+    x, ei = _agg_case(500, 700, 6000, f, f)
+    mean, cnt = osage.scatter_mean(x.index_select(0, ei[0]), ei[1], 700)
+    rel = trg.RelationGraph(ei.to(dev), 500, 700)
+    out, inv_deg = Fn.sage_agg_fwd(rel.fwd, x.to(dev))
+    assert torch.equal(out.cpu(), mean), f"F={f}: max diff {(out.cpu() - mean).abs().max()}"
+    assert torch.equal(inv_deg.cpu(), 1.0 / cnt)
+
+
+def test_agg_fwd_edge_cases(dev):
+    # E = 0, N_src = 0 -> all-zero means (inference.py:412-419)
+    rel = trg.RelationGraph(torch.empty(2, 0, dtype=torch.long, device=dev), 0, 3)
+    out, inv = Fn.sage_agg_fwd(rel.fwd, torch.empty(0, 64, device=dev))
+    assert out.shape == (3, 64) and float(out.abs().sum()) == 0 and inv.tolist() == [1, 1, 1]
+    # N_dst = 0
+    rel = trg.RelationGraph(torch.empty(2, 0, dtype=torch.long, device=dev), 3, 0)
+    out, _ = Fn.sage_agg_fwd(rel.fwd, torch.zeros(3, 64, device=dev))
+    assert out.shape == (0, 64)
+    # a hub destination, duplicates, isolated rows
+    torch.set_num_threads(1)
+    x, ei = _agg_case(300, 50, 20_000, 64, 3, skew=True)
+    ei = torch.cat([ei, ei[:, :500]], dim=1)
+    mean, _ = osage.scatter_mean(x.index_select(0, ei[0]), ei[1], 50)
+    out, _ = Fn.sage_agg_fwd(trg.RelationGraph(ei.to(dev), 300, 50).fwd, x.to(dev))
+    assert torch.equal(out.cpu(), mean)
+
+
+@pytest.mark.parametrize("f", [64, 128, 256])
+def test_agg_fwd_bf16(dev, f):
+    x, ei = _agg_case(400, 600, 5000, f, 100 + f)
+    xb = x.bfloat16()
+    mean, _ = osage.scatter_mean(xb.float().index_select(0, ei[0]), ei[1], 600)
+    out, _ = Fn.sage_agg_fwd(trg.RelationGraph(ei.to(dev), 400, 600).fwd, xb.to(dev))
+    assert out.dtype == torch.bfloat16
+    # fp32 accumulate then one bf16 rounding: error <= 2^-8 relative per element
+    assert_close(out.float().cpu(), mean, TOL_BF16, f"bf16 agg F={f}")
+    assert torch.equal(out.cpu(), mean.bfloat16())  # same fp32 sum, same rounding
+
+
+# ---------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("f,dtype,tol", [(64, torch.float32, TOL_F32), (128, torch.float32, TOL_F32),
+                                         (32, torch.float32, TOL_F32), (128, torch.bfloat16, TOL_BF16)])
+def test_agg_bwd_vs_autograd(dev, f, dtype, tol):
+    x, ei = _agg_case(300, 450, 4000, f, 200 + f, skew=True)
+    x = x.to(dtype).float()
+    g = torch.randn(450, f, generator=torch.Generator().manual_seed(1)).to(dtype).float()
+    xr = x.clone().requires_grad_(True)
+    mean, _ = osage.scatter_mean(xr.index_select(0, ei[0]), ei[1], 450)
+    mean.backward(g)
+    rel = trg.RelationGraph(ei.to(dev), 300, 450)
+    xd = x.to(dev).to(dtype).requires_grad_(True)
+    out = trg.sage_mean_aggregate(xd, rel)
+    out.backward(g.to(dev).to(dtype))
+    assert_close(xd.grad.float().cpu(), xr.grad, tol, "agg bwd")
+
+
+def test_agg_bwd_skipped_for_leaf_features(dev):
+    # layer-1 inputs are constant features -> no transposed CSR is ever built
+    x, ei = _agg_case(50, 60, 300, 64, 5)
+    rel = trg.RelationGraph(ei.to(dev), 50, 60)
+    w = torch.randn(64, 64, device=dev, requires_grad=True)
+    (trg.sage_mean_aggregate(x.to(dev), rel) @ w).sum().backward()
+    assert rel._bwd is None and w.grad is not None
+
+
+# ------------------------------------------------------------------------------------ wsum
+def test_gather_wsum(dev):
+    x, ei = _agg_case(200, 300, 3000, 64, 17)
+    coef = torch.randn(3000, generator=torch.Generator().manual_seed(2))
+    exp = torch.zeros(300, 64, dtype=torch.float64).index_add_(
+        0, ei[1], coef.double()[:, None] * x.double()[ei[0]])
+    csr = trg.RelationGraph(ei.to(dev), 200, 300).fwd
+    scale = torch.tensor([0.5], device=dev)
+    out = Fn.gather_wsum(csr, coef.to(dev), x.to(dev), scale=scale)
+    assert_close(out.cpu(), 0.5 * exp, TOL_F32, "wsum")
+    Fn.gather_wsum(csr, coef.to(dev), x.to(dev), scale=None, out=out, accumulate=True)
+    assert_close(out.cpu(), 1.5 * exp, TOL_F32, "wsum accumulate")
+
+
+# ---------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("h,dtype,tol", [(64, torch.float32, TOL_F32), (128, torch.float32, TOL_F32),
+                                         (16, torch.float32, TOL_F32), (256, torch.float32, TOL_F32),
+                                         (128, torch.bfloat16, TOL_BF16)])
+def test_link_bce_fwd_bwd(dev, h, dtype, tol):
+    U, P, E = 300, 500, 4000
+    g = torch.Generator().manual_seed(h)
+    u = torch.relu(torch.randn(U, h, generator=g)).to(dtype).float()
+    p = torch.relu(torch.randn(P, h, generator=g)).to(dtype).float()
+    tei = torch.stack([torch.randint(0, U, (E,), generator=g), torch.randint(0, P, (E,), generator=g)])
+    tei = torch.cat([tei, tei[:, :50]], dim=1)          # duplicate positives
+    neg = torch.randint(0, P, (tei.size(1),), generator=g)
+    w = torch.zeros(U + P)
+    w[U:] = torch.where(torch.rand(P, generator=g) < 0.25, 3.0, 1.0)
+    ur, pr = u.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    loss = osage.link_loss(ur, pr, tei[0], tei[1], neg, w, U)
+    (2.0 * loss).backward()
+    ud, pd = u.to(dev).to(dtype).requires_grad_(True), p.to(dev).to(dtype).requires_grad_(True)
+    lg = trg.link_bce_loss(ud, pd, tei.to(dev), neg.to(dev), w.to(dev), U)
+    (2.0 * lg).backward()
+    assert abs(float(lg) - float(loss)) <= tol * abs(float(loss)), (float(lg), float(loss))
+    assert_close(ud.grad.float().cpu(), ur.grad, tol, "dL/du")
+    assert_close(pd.grad.float().cpu(), pr.grad, tol, "dL/dp")
+    # forward only (eval): no grads requested
+    with torch.no_grad():
+        l2 = trg.link_bce_loss(ud, pd, tei.to(dev), neg.to(dev), w.to(dev), U)
+    assert float(l2) == float(lg)
+
+
+def test_link_bce_deterministic(dev):
+    U, P, E, h = 200, 300, 5000, 64
+    g = torch.Generator().manual_seed(0)
+    u = torch.randn(U, h, generator=g).to(dev).requires_grad_(True)
+    p = torch.randn(P, h, generator=g).to(dev).requires_grad_(True)
+    tei = torch.stack([torch.randint(0, U, (E,), generator=g), torch.randint(0, P, (E,), generator=g)]).to(dev)
+    neg = torch.randint(0, P, (E,), generator=g).to(dev)
+    w = torch.ones(U + P, device=dev)
+    res = []
+    for _ in range(2):
+        u.grad = p.grad = None
+        l = trg.link_bce_loss(u, p, tei, neg, w, U)
+        l.backward()
+        res.append((l.clone(), u.grad.clone(), p.grad.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*res))   # atomic-free: bitwise repeatable
+
+
+# ---------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("n,h,ks,dtype,tol", [
+    (1000, 64, (64, 64, 64, 64), torch.float32, TOL_F32),
+    (777, 128, (128, 128), torch.float32, TOL_F32),
+    (1, 64, (64, 64, 64, 64), torch.float32, TOL_F32),
+    (300, 32, (16, 48), torch.float32, TOL_F32),
+    (513, 128, (128, 128, 128), torch.bfloat16, TOL_BF16),
+])
+def test_proj_fwd(dev, n, h, ks, dtype, tol):
+    g = torch.Generator().manual_seed(n + h)
+    alphas = [1.0, 1.0, 0.75, 0.75][:len(ks)]
+    terms = [(torch.randn(n, k, generator=g).to(dtype), (torch.randn(h, k, generator=g) / k ** 0.5).to(dtype), a)
+             for k, a in zip(ks, alphas)]
+    bias = torch.randn(h, generator=g)
+    exp = sum(a * (A.double() @ W.double().t()) for A, W, a in terms) + bias.double()
+    for relu in (False, True):
+        out = Fn.sage_proj_fwd([(A.to(dev), W.to(dev), a) for A, W, a in terms], bias.to(dev), relu)
+        e = torch.relu(exp) if relu else exp
+        assert_close(out.float().cpu(), e, tol, f"proj relu={relu}")
+
+
+# ---------------------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("b,p,h,k", [(1, 20_000, 64, 10), (37, 5000, 64, 10), (64, 3000, 128, 100),
+                                     (5, 7, 64, 10), (3, 1000, 16, 3), (130, 2500, 256, 128)])
+def test_score_topk_integer_exact(dev, b, p, h, k):
+    """Small-integer embeddings make every dot product exact in fp32 whatever the summation
+    order, so values AND ids (with massive ties) must equal the canonical oracle bit for bit."""
+    g = torch.Generator().manual_seed(b * p)
+    q = torch.randint(0, 4, (b, h), generator=g).float()
+    cat = torch.randint(0, 3, (p, h), generator=g).float()
+    cat[torch.rand(p, generator=g) < 0.05] = 0          # dead-ReLU rows: exact-zero scores
+    vals, ids = otopk.score_topk(q, cat, k)
+    gv, gi = trg.score_topk(q.to(dev), cat.to(dev), k)
+    assert torch.equal(gv.cpu(), vals) and torch.equal(gi.cpu(), ids)
+    assert torch.equal(gv.cpu(), torch.topk(q @ cat.t(), min(k, p))[0])   # literal torch.topk values
+    gv2, gi2 = trg.score_topk(q.to(dev), cat.to(dev), k, id_offset=1000)
+    assert torch.equal(gi2.cpu(), ids + 1000)
+
+
+def test_score_topk_float_and_sharded(dev):
+    q, cat = synth.synth_queries(50, 30_000, 64, zero_frac=0.05)
+    scores = q @ cat.t()
+    vals, ids = otopk.topk_canonical(scores, 10)
+    gv, gi = trg.score_topk(q.to(dev), cat.to(dev), 10)
+    assert_close(gv.cpu(), vals, TOL_F32, "top-k values")
+    # ids: exact wherever the oracle's neighbouring scores are separated by more than rounding
+    s_at = scores.gather(1, gi.cpu())
+    assert_close(s_at, gv.cpu(), TOL_F32, "scores at returned ids")
+    srt = torch.sort(scores, dim=1, descending=True)[0][:, :11]
+    gap_ok = ((srt[:, :-1] - srt[:, 1:]) > 1e-4 * srt[:, :1]).all(dim=1)
+    assert gap_ok.sum() > 10
+    assert torch.equal(gi.cpu()[gap_ok], ids[gap_ok])
+    # sharded catalogue + merge == unsharded
+    bounds = [(0, 9000), (9000, 21_000), (21_000, 30_000)]
+    parts = [trg.score_topk(q.to(dev), cat[a:b].to(dev).contiguous(), 10, id_offset=a) for a, b in bounds]
+    mv, mi = trg.topk_merge(torch.cat([x[0] for x in parts], 1), torch.cat([x[1] for x in parts], 1), 3, 10)
+    assert torch.equal(mv, gv) and torch.equal(mi, gi)

@@ -1,0 +1,159 @@
+"""GPU parity tests, model level: the drop-in modules run the reference's forward / train() /
+recommendation flow and must match the CPU oracle and the committed golden fixtures."""
+import pytest
+import torch
+
+import truth_recommendation_gnn_b200 as trg
+from oracle import sage as osage
+from oracle import topk as otopk
+from tests.util import TOL_BF16, TOL_F32, assert_close, golden_graph, load_golden, oracle_model
+from truth_recommendation_gnn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_model(h, layers, sd, dev, dtype=torch.float32):
+    m = trg.WeightedRGCN(h) if layers == 1 else trg.StackedWeightedRGCN(h, layers)
+    m.load_state_dict(sd)           # lazy (-1,-1) channels materialise here, like PyG
+    return m.to(dev).to(dtype)
+
+
+def test_sageconv_matches_oracle(dev):
+    g = torch.Generator().manual_seed(0)
+    x_src, x_dst = torch.randn(40, 64, generator=g), torch.randn(30, 64, generator=g)
+    ei = torch.stack([torch.randint(0, 40, (300,), generator=g), torch.randint(0, 30, (300,), generator=g)])
+    ref = osage.SAGEConvOracle((64, 64), 32)
+    conv = trg.SAGEConv((-1, -1), 32)
+    conv.load_state_dict(ref.state_dict())
+    conv = conv.to(dev)
+    out = conv((x_src.to(dev), x_dst.to(dev)), ei.to(dev))
+    assert_close(out.cpu(), ref((x_src, x_dst), ei), TOL_F32, "SAGEConv")
+    # single-tensor form: x -> (x, x)   (train_gnn.py:182 passes (user_x, user_x))
+    ei2 = torch.stack([torch.randint(0, 40, (200,), generator=g), torch.randint(0, 40, (200,), generator=g)])
+    ref2 = osage.SAGEConvOracle(64, 32)
+    conv2 = trg.SAGEConv(64, 32)
+    conv2.load_state_dict(ref2.state_dict())
+    assert_close(conv2.to(dev)(x_src.to(dev), ei2.to(dev)).cpu(), ref2(x_src, ei2), TOL_F32, "SAGEConv(x)")
+
+
+def test_inductive_single_user_empty_graph(dev):
+    """inference.py:410-428: 1 user, 0 posts, empty edge tensors, then mm + topk."""
+    sd = synth.init_state_dict(64, 64)
+    ref = oracle_model(64, 1, sd)
+    model = _gpu_model(64, 1, sd, dev).eval()
+    feat = torch.zeros(1, 64)
+    feat[0, :3] = torch.tensor([1.2, 0.7, 2.3])       # 3 structural features zero-padded to 64
+    empty = torch.empty(2, 0, dtype=torch.long)
+    eid = {osage.REL_DIRECT: empty, osage.REL_SOCIAL: empty, osage.REL_ENGAGE: empty}
+    exp = ref({"user": feat, "post": torch.empty(0, 64)}, eid)["user"]
+    with torch.no_grad():
+        out = model({"user": feat.to(dev), "post": torch.empty(0, 64, device=dev)},
+                    {k: v.to(dev) for k, v in eid.items()})
+    assert out["post"].shape == (0, 64)
+    assert_close(out["user"].cpu(), exp, TOL_F32, "inductive user embedding")
+    _, cat = synth.synth_queries(1, 5000, 64)
+    vals, ids = otopk.score_topk(exp, cat, 10)
+    gv, gi = trg.recommend(out["user"], cat.to(dev), k=10)
+    assert_close(gv.cpu(), vals, TOL_F32, "top-10 scores")
+    assert torch.equal(gi.cpu(), ids)
+
+
+@pytest.mark.parametrize("name", ["tiny_l1", "small_l2", "small_l1_skew"])
+def test_golden_forward_train_topk(dev, name):
+    fix = load_golden(name)
+    m = fix["meta"]
+    g = golden_graph(fix, dev)
+    model = _gpu_model(m["h"], m["layers"], fix["state_dict"], dev)
+    with torch.no_grad():
+        out = model(g.x_dict, g.edge_index_dict)
+    assert_close(out["user"].cpu(), fix["out0_user"], TOL_F32, "user emb")
+    assert_close(out["post"].cpu(), fix["out0_post"], TOL_F32, "post emb")
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    for s in range(m["steps"]):
+        loss = trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
+                              g.interaction_type_tensor, m["u"], m["p"], neg_p=fix["neg"][s].to(dev))
+        ref = float(fix["losses"][s])
+        assert abs(loss - ref) <= TOL_F32 * abs(ref), (s, loss, ref)
+    for n, p in model.named_parameters():
+        assert_close(p.grad.cpu(), fix["last_grads"][n], 5 * TOL_F32, f"grad {n}")
+    with torch.no_grad():
+        out1 = model(g.x_dict, g.edge_index_dict)
+    assert_close(out1["user"].cpu(), fix["out1_user"], 5 * TOL_F32, "user emb after training")
+    gv, gi = trg.recommend(out1["user"], out1["post"], k=m["k"])
+    assert_close(gv.cpu(), fix["topk_vals"], 5 * TOL_F32, "top-k scores")
+    # ids must agree wherever the oracle's ranking is not a near-tie
+    sc = fix["out1_user"] @ fix["out1_post"].t()
+    srt = torch.sort(sc, dim=1, descending=True)[0][:, :m["k"] + 1]
+    ok = ((srt[:, :-1] - srt[:, 1:]) > 1e-4 * srt[:, :1].abs().clamp(min=1e-6)).all(dim=1)
+    assert torch.equal(gi.cpu()[ok], fix["topk_ids"][ok])
+    for rel, c in fix["csr"].items():
+        r = eval(rel)
+        rg = trg.relation_graph(g.edge_index_dict[r], g.x_dict[r[0]].size(0), g.x_dict[r[2]].size(0))
+        assert torch.equal(rg.fwd.rowptr.cpu(), c["rowptr"]) and torch.equal(rg.fwd.col.cpu(), c["col"])
+        assert torch.equal(rg.fwd.eid.cpu(), c["eid"])
+
+
+def test_train_trajectory_cfg1_scaled(dev):
+    """Same state_dict, same negatives, 5 Adam steps on a config-1-shaped graph (scaled 1/10):
+    loss trajectory, final weights and embeddings against the oracle."""
+    torch.set_num_threads(8)
+    U, P, H, L = 1000, 5000, 64, 2
+    g = synth.synth_graph(U, P, 40_000, 10_000, H, seed=0)
+    sd = synth.init_state_dict(H, H, L)
+    ref = oracle_model(H, L, sd)
+    model = _gpu_model(H, L, sd, dev)
+    gd = g.to(dev)
+    o_ref, o_gpu = torch.optim.Adam(ref.parameters(), lr=1e-3), torch.optim.Adam(model.parameters(), lr=1e-3)
+    for s in range(5):
+        neg = synth.synth_neg(P, 40_000, s)
+        lr = osage.train_step(ref, o_ref, g.x_dict, g.edge_index_dict, g.train_edge_index,
+                              g.interaction_type_tensor, U, P, neg_p=neg)
+        lg = trg.train_step(model, o_gpu, gd.x_dict, gd.edge_index_dict, gd.train_edge_index,
+                            gd.interaction_type_tensor, U, P, neg_p=neg.to(dev))
+        assert abs(lg - lr) <= TOL_F32 * abs(lr), (s, lg, lr)
+    for (n, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
+        assert_close(a.detach().cpu(), b.detach(), 1e-4, f"param {n} after 5 steps")
+
+
+def test_bf16_forward_and_step(dev):
+    U, P, H, L = 800, 3000, 128, 2
+    g = synth.synth_graph(U, P, 30_000, 8000, H, seed=1)
+    sd = synth.init_state_dict(H, H, L)
+    sd_b = {k: v.bfloat16().float() for k, v in sd.items()}
+    ref = oracle_model(H, L, sd_b)                      # fp32 oracle on bf16-rounded inputs/weights
+    xb = {k: v.bfloat16().float() for k, v in g.x_dict.items()}
+    with torch.no_grad():
+        exp = ref(xb, g.edge_index_dict)
+    model = _gpu_model(H, L, sd, dev, torch.bfloat16)
+    gd = g.to(dev)
+    xd = {k: v.bfloat16() for k, v in gd.x_dict.items()}
+    with torch.no_grad():
+        out = model(xd, gd.edge_index_dict)
+    assert out["user"].dtype == torch.bfloat16
+    assert_close(out["user"].float().cpu(), exp["user"], 2 * TOL_BF16, "bf16 user emb (2 layers)")
+    assert_close(out["post"].float().cpu(), exp["post"], 2 * TOL_BF16, "bf16 post emb (2 layers)")
+    neg = synth.synth_neg(P, 30_000, 0)
+    lref = osage.link_loss(exp["user"], exp["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
+                           g.interaction_type_tensor, U)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    lg = trg.train_step(model, opt, xd, gd.edge_index_dict, gd.train_edge_index,
+                        gd.interaction_type_tensor, U, P, neg_p=neg.to(dev))
+    assert abs(lg - float(lref)) <= TOL_BF16 * abs(float(lref))
+
+
+def test_multi_layer_needs_transposed_backward(dev):
+    """Layers >= 2 exercise K2 (transposed-CSR backward); compare all weight grads with autograd
+    through the oracle."""
+    U, P, H, L = 300, 700, 32, 3
+    g = synth.synth_graph(U, P, 6000, 1500, H, seed=3, skew=True)
+    sd = synth.init_state_dict(H, H, L)
+    ref, model = oracle_model(H, L, sd), _gpu_model(H, L, sd, dev)
+    neg = synth.synth_neg(P, 6000, 0)
+    out = ref(g.x_dict, g.edge_index_dict)
+    osage.link_loss(out["user"], out["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
+                    g.interaction_type_tensor, U).backward()
+    gd = g.to(dev)
+    o = model(gd.x_dict, gd.edge_index_dict)
+    trg.link_bce_loss(o["user"], o["post"], gd.train_edge_index, neg.to(dev), gd.interaction_type_tensor, U).backward()
+    for (n, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
+        assert_close(a.grad.cpu(), b.grad, 5 * TOL_F32, f"grad {n}")

@@ -1,0 +1,98 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the drop-in modules keep the reference's API contract, and nothing silently falls back
+to the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import truth_recommendation_gnn_b200 as trg
+from truth_recommendation_gnn_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "trg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(trg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _declared_symbols()
+    assert len(syms) >= 12
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/trg_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "python binding and header disagree"
+    assert _lib.load().trg_abi_version() == 1
+    assert _lib.load().trg_csr_workspace_bytes(1000, 100) > 4 * 4 * 1000
+
+
+def test_no_cpu_fallback():
+    conv = trg.SAGEConv((8, 8), 4)
+    with pytest.raises(_lib.TrgError):
+        conv((torch.zeros(2, 8), torch.zeros(3, 8)), torch.zeros(2, 0, dtype=torch.long))
+    with pytest.raises(_lib.TrgError):
+        trg.score_topk(torch.zeros(1, 8), torch.zeros(4, 8), 2)
+    with pytest.raises(_lib.TrgError):
+        trg.build_csr(torch.zeros(3, dtype=torch.long), torch.zeros(3, dtype=torch.long), 2, 2, validate=False)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "truth_recommendation_gnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_lazy_parameters_and_state_dict_contract():
+    # train_gnn.py:206-207: optimizer is built before the first forward on lazily-shaped params
+    model = trg.WeightedRGCN(hidden_dim=64)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ids = [id(p) for p in model.parameters()]
+    keys = list(model.state_dict().keys())
+    assert keys == [f"{c}.{p}" for c in ("msg_direct", "msg_social", "post_update")
+                    for p in ("lin_l.weight", "lin_l.bias", "lin_r.weight")]
+    sd = synth.init_state_dict(64, 64)
+    model.load_state_dict(sd)                         # strict, materialises in place
+    assert ids == [id(p) for p in model.parameters()]
+    assert all(torch.equal(model.state_dict()[k], sd[k]) for k in sd)
+    assert sum(p.numel() for p in model.parameters()) == 24768
+    assert len(opt.param_groups[0]["params"]) == 9
+    stacked = trg.StackedWeightedRGCN(32, 3, in_channels=(16, 16))
+    assert stacked.layers[0].msg_direct.lin_l.weight.shape == (32, 16)
+    assert stacked.layers[2].post_update.lin_r.weight.shape == (32, 32)
+    stacked.load_state_dict(synth.init_state_dict(32, 16, 3))
+
+
+def test_sageconv_rejects_unaccelerated_options():
+    with pytest.raises(NotImplementedError):
+        trg.SAGEConv((-1, -1), 8, aggr="max")
+    with pytest.raises(NotImplementedError):
+        trg.SAGEConv((-1, -1), 8, normalize=True)
+
+
+def test_linear_default_init_matches_torch():
+    torch.manual_seed(0)
+    a = trg.Linear(16, 8)
+    torch.manual_seed(0)
+    b = torch.nn.Linear(16, 8)
+    assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)
+
+
+def test_synth_is_deterministic_and_in_reference_format():
+    g1 = synth.synth_graph(30, 50, 200, 60, 8, seed=0)
+    g2 = synth.synth_graph(30, 50, 200, 60, 8, seed=0)
+    for k in g1.edge_index_dict:
+        assert torch.equal(g1.edge_index_dict[k], g2.edge_index_dict[k])
+        assert g1.edge_index_dict[k].dtype == torch.int64 and g1.edge_index_dict[k].shape[0] == 2
+    assert torch.equal(g1.edge_index_dict[synth.REL_DIRECT], g1.edge_index_dict[synth.REL_ENGAGE].flip(0))
+    assert torch.allclose(g1.x_dict["user"].norm(dim=1), torch.ones(30), atol=1e-6)
+    assert g1.mp_edges == 2 * 200 + 60
+    w = g1.interaction_type_tensor
+    assert w.shape == (80,) and set(w[30:].tolist()) <= {1.0, 3.0} and float(w[:30].abs().sum()) == 0.0

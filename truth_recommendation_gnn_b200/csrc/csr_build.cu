@@ -1,0 +1,320 @@
+// K0 -- destination-sorted CSR builder (trg_csr_build): stable LSD radix sort of the COO edge
+// list by key + degree histogram + exclusive scan.  HBM-bound integer work; bit-exact with
+// argsort(key, stable) / bincount / cumsum (oracle/csr.py).
+//
+// Replaces: the COO edge_index consumption of PyG's propagate for the tensors built at
+// build_graph.py:387,394,402 and train_gnn.py:128-142 (reference keeps COO and scatters with
+// atomics; a stable sort once per static graph makes every later pass atomic-free).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace trg {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;  // 4096 keys per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kRadix = 256;
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of int32 arrays (3 launches: tile sums, scan of tile sums, apply)
+// ---------------------------------------------------------------------------------------------
+template <int NWARPS>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  int ws = (lane < NWARPS) ? warp_sums[lane] : 0;
+  int winc = ws;
+#pragma unroll
+  for (int o = 1; o < NWARPS; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, winc, o);
+    if (lane >= o) winc += t;
+  }
+  const int wbase = __shfl_sync(0xffffffffu, winc - ws, w);
+  total = __shfl_sync(0xffffffffu, winc, NWARPS - 1);
+  __syncthreads();
+  return wbase + inc - v;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_tile_sums(const int* __restrict__ in, int64_t n,
+                                                           int* __restrict__ tile_sums) {
+  __shared__ int warp_sums[kWarps];
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    int64_t idx = base + (int64_t)i * kThreads + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  int total;
+  block_exclusive_scan<kWarps>(s, warp_sums, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_offsets(int* __restrict__ tile_sums, int n_tiles) {
+  __shared__ int warp_sums[32];
+  int carry = 0;
+  for (int base = 0; base < n_tiles; base += 1024) {
+    int idx = base + threadIdx.x;
+    int v = idx < n_tiles ? tile_sums[idx] : 0;
+    int total;
+    int ex = block_exclusive_scan<32>(v, warp_sums, total);
+    if (idx < n_tiles) tile_sums[idx] = carry + ex;
+    carry += total;
+  }
+}
+
+// in-place capable: every thread reads its items before any thread of the CTA writes them.
+__global__ void __launch_bounds__(kThreads) scan_apply(const int* in, int* out, int64_t n,
+                                                       const int* __restrict__ tile_offsets) {
+  __shared__ int warp_sums[kWarps];
+  const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
+  int v[kItems];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  int total;
+  int run = block_exclusive_scan<kWarps>(s, warp_sums, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+}
+
+int exclusive_scan(const int* in, int* out, int64_t n, int* tile_sums, cudaStream_t st) {
+  if (n <= 0) return TRG_OK;
+  const int n_tiles = (int)ceil_div<int64_t>(n, kTile);
+  scan_tile_sums<<<n_tiles, kThreads, 0, st>>>(in, n, tile_sums);
+  scan_tile_offsets<<<1, 1024, 0, st>>>(tile_sums, n_tiles);
+  scan_apply<<<n_tiles, kThreads, 0, st>>>(in, out, n, tile_sums);
+  count_launch(3);
+  TRG_LAUNCH_OK();
+  return TRG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// degree histogram
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) count_keys(const long long* __restrict__ key, int64_t n,
+                                                       int* __restrict__ deg) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) atomicAdd(&deg[(int)ldg_stream(key + i)], 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one LSD pass: per-CTA digit histogram -> global scan -> stable scatter
+// ---------------------------------------------------------------------------------------------
+template <bool FIRST>
+__device__ __forceinline__ uint32_t load_key(const void* keys, int64_t idx) {
+  if (FIRST) return (uint32_t)ldg_stream(reinterpret_cast<const long long*>(keys) + idx);
+  return (uint32_t)ldg_stream(reinterpret_cast<const int*>(keys) + idx);
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kThreads) radix_hist(const void* __restrict__ keys, int64_t n,
+                                                       int shift, int* __restrict__ hist,
+                                                       int n_ctas) {
+  __shared__ int h[kRadix];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    int64_t idx = base + (int64_t)i * kThreads + threadIdx.x;
+    if (idx < n) atomicAdd(&h[(load_key<FIRST>(keys, idx) >> shift) & (kRadix - 1)], 1);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * n_ctas + blockIdx.x] = h[threadIdx.x];
+}
+
+// Stability: warp w owns the contiguous span [w*512, w*512+512) of the tile and walks it 32 keys
+// at a time; a key's rank among equal digits = (earlier CTAs) + (earlier warps) + (earlier
+// rounds of this warp) + (lower lanes of this round, via match_any).
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kThreads)
+    radix_scatter(const void* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
+                  int shift, const int* __restrict__ gbase, int n_ctas,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ int wcnt[kWarps][kRadix];
+  __shared__ int sbase[kRadix];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) wcnt[i][threadIdx.x] = 0;
+  const int64_t wbase = (int64_t)blockIdx.x * kTile + (int64_t)w * (kItems * 32);
+
+  uint32_t key[kItems], val[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int64_t idx = wbase + r * 32 + lane;
+    bool valid = idx < n;
+    key[r] = valid ? load_key<FIRST>(keys_in, idx) : 0u;
+    val[r] = FIRST ? (uint32_t)idx : (valid ? (uint32_t)ldg_stream((const int*)vals_in + idx) : 0u);
+  }
+  __syncthreads();
+
+  int rank[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const bool valid = wbase + r * 32 + lane < n;
+    const int d = valid ? (int)((key[r] >> shift) & (kRadix - 1)) : kRadix;  // sentinel never matches
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int prev = valid ? wcnt[w][d] : 0;
+    __syncwarp();
+    if (valid && lane == __ffs(peers) - 1) wcnt[w][d] = prev + __popc(peers);
+    __syncwarp();
+    rank[r] = prev + __popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  {
+    int run = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) {
+      int t = wcnt[i][threadIdx.x];
+      wcnt[i][threadIdx.x] = run;
+      run += t;
+    }
+    sbase[threadIdx.x] = gbase[(int64_t)threadIdx.x * n_ctas + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    if (wbase + r * 32 + lane < n) {
+      const int d = (int)((key[r] >> shift) & (kRadix - 1));
+      const int dest = sbase[d] + wcnt[w][d] + rank[r];
+      if (!LAST) keys_out[dest] = key[r];
+      vals_out[dest] = val[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gather_col(const long long* __restrict__ other,
+                                                       const int* __restrict__ eid, int64_t n,
+                                                       int* __restrict__ col) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) col[i] = (int)other[ldg_stream(eid + i)];
+}
+
+int num_passes(int64_t n_key) {
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) < n_key) ++bits;
+  return (bits + 7) / 8;
+}
+
+struct Workspace {
+  uint32_t *keys[2], *vals[2];
+  int *hist, *tile_sums;
+  size_t bytes;
+};
+
+Workspace carve(void* ws, int64_t e, int64_t n_key) {
+  Workspace w;
+  const size_t ebytes = align_up((size_t)(e > 0 ? e : 1) * 4, 256);
+  const int64_t n_ctas = ceil_div<int64_t>(e > 0 ? e : 1, kTile);
+  const size_t hist_bytes = align_up((size_t)kRadix * n_ctas * 4, 256);
+  const int64_t scan_len = (int64_t)kRadix * n_ctas > n_key + 1 ? (int64_t)kRadix * n_ctas : n_key + 1;
+  const size_t sums_bytes = align_up((size_t)ceil_div<int64_t>(scan_len, kTile) * 4 + 4, 256);
+  char* p = reinterpret_cast<char*>(ws);
+  w.keys[0] = (uint32_t*)p; p += ebytes;
+  w.keys[1] = (uint32_t*)p; p += ebytes;
+  w.vals[0] = (uint32_t*)p; p += ebytes;
+  w.vals[1] = (uint32_t*)p; p += ebytes;
+  w.hist = (int*)p; p += hist_bytes;
+  w.tile_sums = (int*)p; p += sums_bytes;
+  w.bytes = (size_t)(p - reinterpret_cast<char*>(ws));
+  return w;
+}
+
+}  // namespace
+}  // namespace trg
+
+using namespace trg;
+
+extern "C" size_t trg_csr_workspace_bytes(int64_t n_edges, int64_t n_key) {
+  if (n_edges < 0 || n_key < 0) return 0;
+  return carve(nullptr, n_edges, n_key).bytes;
+}
+
+extern "C" int trg_csr_build(const int64_t* other, const int64_t* key, int64_t e, int64_t n_key,
+                             int32_t* rowptr, int32_t* col, int32_t* eid, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  TRG_CHECK_ARG(e >= 0 && n_key >= 0, "trg_csr_build: negative size");
+  TRG_CHECK_ARG(e < ((int64_t)1 << 31) && n_key < ((int64_t)1 << 31) - 1,
+                "trg_csr_build: n_edges=%lld / n_key=%lld exceed int32 CSR range", (long long)e,
+                (long long)n_key);
+  TRG_CHECK_ARG(rowptr != nullptr, "trg_csr_build: rowptr is NULL");
+  TRG_CHECK_ARG(e == 0 || (key != nullptr && (col == nullptr || other != nullptr)),
+                "trg_csr_build: NULL edge arrays with n_edges > 0");
+  TRG_CHECK_ARG(e == 0 || n_key > 0, "trg_csr_build: edges present but n_key == 0");
+  Workspace w = carve(workspace, e, n_key);
+  if (workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("trg_csr_build: workspace %zu < required %zu", workspace_bytes, w.bytes);
+    return TRG_E_WORKSPACE;
+  }
+  TRG_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(n_key + 1) * sizeof(int32_t), st));
+  if (e == 0) return TRG_OK;
+
+  // degrees -> rowptr (exclusive scan over n_key + 1 entries; entry n_key is 0 -> rowptr[n_key] = E)
+  {
+    int grid = (int)std::min<int64_t>(ceil_div<int64_t>(e, kThreads), (int64_t)kNumSMs * 16);
+    count_keys<<<grid, kThreads, 0, st>>>((const long long*)key, e, rowptr);
+    count_launch();
+    TRG_LAUNCH_OK();
+    int rc = exclusive_scan(rowptr, rowptr, n_key + 1, w.tile_sums, st);
+    if (rc) return rc;
+  }
+  if (col == nullptr && eid == nullptr) return TRG_OK;
+
+  const int passes = num_passes(n_key);
+  const int n_ctas = (int)ceil_div<int64_t>(e, kTile);
+  const void* kin = key;
+  const uint32_t* vin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const bool first = p == 0, last = p == passes - 1;
+    const int shift = 8 * p;
+    uint32_t* kout = w.keys[p & 1];
+    uint32_t* vout = last ? (eid ? (uint32_t*)eid : w.vals[p & 1]) : w.vals[p & 1];
+    if (first)
+      radix_hist<true><<<n_ctas, kThreads, 0, st>>>(kin, e, shift, w.hist, n_ctas);
+    else
+      radix_hist<false><<<n_ctas, kThreads, 0, st>>>(kin, e, shift, w.hist, n_ctas);
+    count_launch();
+    TRG_LAUNCH_OK();
+    int rc = exclusive_scan(w.hist, w.hist, (int64_t)kRadix * n_ctas, w.tile_sums, st);
+    if (rc) return rc;
+    if (first && last)
+      radix_scatter<true, true><<<n_ctas, kThreads, 0, st>>>(kin, vin, e, shift, w.hist, n_ctas, kout, vout);
+    else if (first)
+      radix_scatter<true, false><<<n_ctas, kThreads, 0, st>>>(kin, vin, e, shift, w.hist, n_ctas, kout, vout);
+    else if (last)
+      radix_scatter<false, true><<<n_ctas, kThreads, 0, st>>>(kin, vin, e, shift, w.hist, n_ctas, kout, vout);
+    else
+      radix_scatter<false, false><<<n_ctas, kThreads, 0, st>>>(kin, vin, e, shift, w.hist, n_ctas, kout, vout);
+    count_launch();
+    TRG_LAUNCH_OK();
+    kin = kout;
+    vin = vout;
+  }
+  if (col != nullptr) {
+    int grid = (int)std::min<int64_t>(ceil_div<int64_t>(e, kThreads), (int64_t)kNumSMs * 16);
+    gather_col<<<grid, kThreads, 0, st>>>((const long long*)other, (const int*)vin, e, col);
+    count_launch();
+    TRG_LAUNCH_OK();
+  }
+  return TRG_OK;
+}

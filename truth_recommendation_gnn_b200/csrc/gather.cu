@@ -1,0 +1,237 @@
+// K1 / K2 -- fused neighbour gather + segmented reduction over a destination-sorted CSR.
+//
+//   trg_sage_agg_fwd : mean[r] = (sum_{j in row r} x[col[j]]) / max(deg r, 1)
+//                      replaces x_src.index_select(0, src) + scatter(reduce='mean') inside the
+//                      SAGEConv calls at train_gnn.py:177-184,194-197 (never materialises [E,F]).
+//   trg_sage_agg_bwd : g_src[s] = sum_{j in row s of the transposed CSR} g_mean[c] * inv_deg[c]
+//                      replaces autograd's index_add/gather; atomic-free.
+//   trg_gather_wsum  : out[r] (+)= scale * sum_j coef[eid[j]] * x[col[j]]  (loss backward).
+//
+// HBM-bound: one group of LPR lanes owns one destination row; each lane moves 16-byte vectors
+// of the gathered source rows (coalesced across the group: a 512 B fp32 H=128 row is one
+// LDG.128 per lane of a full warp) with up to 8 row loads in flight per lane; neighbour ids are
+// read coalesced (one per lane) and broadcast by shuffle.  Neighbours are added in CSR order,
+// which is edge order inside a row (stable sort), so fp32 sums equal the CPU scatter_add_ bit
+// for bit.
+#include "common.cuh"
+
+namespace trg {
+namespace {
+
+constexpr int kThreads = 256;
+
+enum Mode { kMean = 0, kNbrScale = 1, kEdgeCoef = 2 };
+
+struct GatherArgs {
+  const int* rowptr;
+  const int* col;
+  const int* eid;          // kEdgeCoef
+  const float* coef;       // kEdgeCoef: indexed by eid
+  const float* nbr_scale;  // kNbrScale: indexed by col (nullable)
+  const float* scale;      // device scalar, nullable
+  const void* x;
+  void* out;
+  float* inv_deg_out;  // kMean, nullable
+  int64_t n_rows;
+  int row_vecs;  // 16-byte vectors per row
+  int accumulate;
+};
+
+template <typename T, int LPR, int VPL, int MODE>
+__global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
+  constexpr int kVec = Elem<T>::kVec;
+  constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPR - 1);
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / LPR) + threadIdx.x / LPR;
+  if (row >= a.n_rows) return;
+
+  const int beg = ldg_stream(a.rowptr + row);
+  const int end = ldg_stream(a.rowptr + row + 1);
+  const size_t row_bytes = (size_t)a.row_vecs * 16;
+  const char* xb = reinterpret_cast<const char*>(a.x);
+
+  bool act[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) act[i] = gl + i * LPR < a.row_vecs;
+
+  float acc[VPL][kVec];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) acc[i][k] = 0.f;
+
+  for (int j = beg; j < end; j += LPR) {
+    const int my = j + gl;
+    int c = 0;
+    float wgt = 1.f;
+    if (my < end) {
+      c = ldg_stream(a.col + my);
+      if (MODE == kNbrScale) {
+        if (a.nbr_scale) wgt = __ldg(a.nbr_scale + c);
+      } else if (MODE == kEdgeCoef) {
+        wgt = __ldg(a.coef + ldg_stream(a.eid + my));
+      }
+    }
+    const int cnt = min(LPR, end - j);
+    for (int t = 0; t < cnt; t += kUnroll) {
+      uint4 v[kUnroll][VPL];
+      float wv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        // shuffles are executed by the whole group (cnt is group-uniform)
+        const int cu = __shfl_sync(gmask, c, t + u, LPR);
+        if (MODE != kMean) wv[u] = __shfl_sync(gmask, wgt, t + u, LPR);
+        if (t + u < cnt) {
+          const char* rp = xb + (size_t)cu * row_bytes + (size_t)gl * 16;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i)
+            if (act[i]) v[u][i] = ldg_row(rp + (size_t)i * LPR * 16);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (t + u < cnt) {
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            if (act[i]) {
+              float f[kVec];
+              Elem<T>::unpack(v[u][i], f);
+#pragma unroll
+              for (int k = 0; k < kVec; ++k) {
+                if (MODE == kMean)
+                  acc[i][k] = __fadd_rn(acc[i][k], f[k]);  // plain adds, CSR order: bit-exact
+                else
+                  acc[i][k] = fmaf(wv[u], f[k], acc[i][k]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  float post = 1.f;
+  if (MODE == kMean) {
+    const float cntf = (float)max(end - beg, 1);
+    if (gl == 0 && a.inv_deg_out) a.inv_deg_out[row] = __fdiv_rn(1.f, cntf);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) acc[i][k] = __fdiv_rn(acc[i][k], cntf);  // sum / count (IEEE)
+  } else if (a.scale) {
+    post = __ldg(a.scale);
+  }
+  char* ob = reinterpret_cast<char*>(a.out) + (size_t)row * row_bytes + (size_t)gl * 16;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (!act[i]) continue;
+    if (MODE != kMean) {
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) acc[i][k] *= post;
+      if (a.accumulate) {
+        float f[kVec];
+        Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)i * LPR * 16), f);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
+      }
+    }
+    stg_stream(ob + (size_t)i * LPR * 16, Elem<T>::pack(acc[i]));
+  }
+}
+
+template <typename T, int MODE>
+int launch_gather(const GatherArgs& a, cudaStream_t st) {
+  if (a.n_rows == 0) return TRG_OK;
+  const int rv = a.row_vecs;
+#define TRG_GATHER_CASE(LPR, VPL)                                                         \
+  {                                                                                       \
+    const int64_t grid = ceil_div<int64_t>(a.n_rows, kThreads / LPR);                     \
+    gather_reduce<T, LPR, VPL, MODE><<<(unsigned)grid, kThreads, 0, st>>>(a);             \
+  }
+  if (rv <= 1) TRG_GATHER_CASE(1, 1)
+  else if (rv <= 2) TRG_GATHER_CASE(2, 1)
+  else if (rv <= 4) TRG_GATHER_CASE(4, 1)
+  else if (rv <= 8) TRG_GATHER_CASE(8, 1)
+  else if (rv <= 16) TRG_GATHER_CASE(16, 1)
+  else if (rv <= 32) TRG_GATHER_CASE(32, 1)
+  else if (rv <= 64) TRG_GATHER_CASE(32, 2)
+  else if (rv <= 128) TRG_GATHER_CASE(32, 4)
+  else {
+    set_error("gather: rows wider than 2048 bytes are not supported (row_vecs=%d)", rv);
+    return TRG_E_UNSUPPORTED;
+  }
+#undef TRG_GATHER_CASE
+  count_launch();
+  TRG_LAUNCH_OK();
+  return TRG_OK;
+}
+
+template <int MODE>
+int dispatch(const GatherArgs& a, int dtype, cudaStream_t st) {
+  if (dtype == TRG_F32) return launch_gather<float, MODE>(a, st);
+  if (dtype == TRG_BF16) return launch_gather<__nv_bfloat16, MODE>(a, st);
+  set_error("gather: unknown dtype %d", dtype);
+  return TRG_E_ARG;
+}
+
+int row_vecs_of(int feat, int dtype, const char* who, int* out) {
+  const int es = dtype == TRG_BF16 ? 2 : 4;
+  if (feat <= 0 || (feat * es) % 16 != 0) {
+    set_error("%s: row width %d x %d bytes is not a multiple of 16 bytes", who, feat, es);
+    return TRG_E_ARG;
+  }
+  *out = feat * es / 16;
+  return TRG_OK;
+}
+
+}  // namespace
+}  // namespace trg
+
+using namespace trg;
+
+extern "C" int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_src,
+                                int64_t n_dst, int32_t feat, int dtype, void* mean_out,
+                                float* inv_deg_out, void* stream) {
+  TRG_CHECK_ARG(n_dst >= 0, "trg_sage_agg_fwd: n_dst < 0");
+  if (n_dst == 0) return TRG_OK;
+  TRG_CHECK_ARG(rowptr && mean_out, "trg_sage_agg_fwd: NULL rowptr/out");
+  TRG_CHECK_ARG(((uintptr_t)x_src | (uintptr_t)mean_out) % 16 == 0, "trg_sage_agg_fwd: tables must be 16-byte aligned");
+  GatherArgs a{};
+  int rc = row_vecs_of(feat, dtype, "trg_sage_agg_fwd", &a.row_vecs);
+  if (rc) return rc;
+  a.rowptr = rowptr; a.col = col; a.x = x_src; a.out = mean_out; a.inv_deg_out = inv_deg_out;
+  a.n_rows = n_dst;
+  return dispatch<kMean>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
+                                const void* g_mean, int64_t n_src, int32_t feat, int dtype,
+                                void* g_src_out, void* stream) {
+  TRG_CHECK_ARG(n_src >= 0, "trg_sage_agg_bwd: n_src < 0");
+  if (n_src == 0) return TRG_OK;
+  TRG_CHECK_ARG(rowptr_t && g_src_out, "trg_sage_agg_bwd: NULL rowptr/out");
+  TRG_CHECK_ARG(((uintptr_t)g_mean | (uintptr_t)g_src_out) % 16 == 0, "trg_sage_agg_bwd: tables must be 16-byte aligned");
+  GatherArgs a{};
+  int rc = row_vecs_of(feat, dtype, "trg_sage_agg_bwd", &a.row_vecs);
+  if (rc) return rc;
+  a.rowptr = rowptr_t; a.col = col_t; a.nbr_scale = inv_deg; a.x = g_mean; a.out = g_src_out;
+  a.n_rows = n_src;
+  return dispatch<kNbrScale>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                               const float* coef, const float* scale, const void* x, int64_t n_rows,
+                               int32_t feat, int dtype, void* out, int accumulate, void* stream) {
+  TRG_CHECK_ARG(n_rows >= 0, "trg_gather_wsum: n_rows < 0");
+  if (n_rows == 0) return TRG_OK;
+  TRG_CHECK_ARG(rowptr && out, "trg_gather_wsum: NULL rowptr/out");
+  TRG_CHECK_ARG(((uintptr_t)x | (uintptr_t)out) % 16 == 0, "trg_gather_wsum: tables must be 16-byte aligned");
+  GatherArgs a{};
+  int rc = row_vecs_of(feat, dtype, "trg_gather_wsum", &a.row_vecs);
+  if (rc) return rc;
+  a.rowptr = rowptr; a.col = col; a.eid = eid; a.coef = coef; a.scale = scale; a.x = x; a.out = out;
+  a.n_rows = n_rows; a.accumulate = accumulate;
+  return dispatch<kEdgeCoef>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+}

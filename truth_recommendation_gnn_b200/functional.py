@@ -1,0 +1,254 @@
+"""``torch.autograd.Function`` wrappers around the C ABI (include/trg_b200.h).
+
+Each function names the reference lines it replaces; all arithmetic on the hot path happens in
+the sm_100a kernels -- torch supplies memory, the stream and the autograd tape.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .graph import CSR, RelationGraph, build_csr
+
+
+def _check_rows(x: torch.Tensor, what: str):
+    es = x.element_size()
+    if x.dim() != 2 or (x.size(1) * es) % 16 != 0:
+        raise _lib.TrgError(f"{what}: rows must be a multiple of 16 bytes (got shape {tuple(x.shape)}, "
+                            f"{x.dtype}); pad the feature width (the reference pads to 64, inference.py:401-404)")
+
+
+# ------------------------------------------------------------------------------------------
+# K1 / K2: SAGEConv propagate + mean aggregation
+# ------------------------------------------------------------------------------------------
+def sage_agg_fwd(csr: CSR, x_src: torch.Tensor, want_inv_deg: bool = True):
+    """mean over in-neighbours (train_gnn.py:177-184,194-197 -> PyG propagate/MeanAggregation)."""
+    lib = _lib.load()
+    _check_rows(x_src, "sage_agg_fwd")
+    x_src = x_src.contiguous()
+    out = torch.empty(csr.n_rows, x_src.size(1), dtype=x_src.dtype, device=x_src.device)
+    inv_deg = torch.empty(csr.n_rows, dtype=torch.float32, device=x_src.device) if want_inv_deg else None
+    if csr.n_rows:
+        _lib.check(lib.trg_sage_agg_fwd(_lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(x_src),
+                                        csr.n_rows, x_src.size(1), _lib.dtype_code(x_src.dtype),
+                                        _lib.ptr(out), _lib.ptr(inv_deg), _lib.stream()),
+                   "trg_sage_agg_fwd")
+    return out, inv_deg
+
+
+def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor):
+    """Atomic-free gradient w.r.t. the source table through the transposed CSR."""
+    lib = _lib.load()
+    g_mean = g_mean.contiguous()
+    _check_rows(g_mean, "sage_agg_bwd")
+    out = torch.empty(csr_t.n_rows, g_mean.size(1), dtype=g_mean.dtype, device=g_mean.device)
+    if csr_t.n_rows:
+        _lib.check(lib.trg_sage_agg_bwd(_lib.ptr(csr_t.rowptr), _lib.ptr(csr_t.col), _lib.ptr(inv_deg),
+                                        _lib.ptr(g_mean), csr_t.n_rows, g_mean.size(1),
+                                        _lib.dtype_code(g_mean.dtype), _lib.ptr(out), _lib.stream()),
+                   "trg_sage_agg_bwd")
+    return out
+
+
+class SageAggFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_src, rel: RelationGraph):
+        mean, inv_deg = sage_agg_fwd(rel.fwd, x_src)
+        ctx.rel = rel
+        ctx.save_for_backward(inv_deg)
+        return mean
+
+    @staticmethod
+    def backward(ctx, g_mean):
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        (inv_deg,) = ctx.saved_tensors
+        return sage_agg_bwd(ctx.rel.bwd, inv_deg, g_mean), None
+
+
+def sage_mean_aggregate(x_src: torch.Tensor, rel: RelationGraph) -> torch.Tensor:
+    return SageAggFn.apply(x_src, rel)
+
+
+# ------------------------------------------------------------------------------------------
+# generic weighted gather-sum
+# ------------------------------------------------------------------------------------------
+def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulate=False):
+    lib = _lib.load()
+    x = x.contiguous()
+    _check_rows(x, "gather_wsum")
+    if out is None:
+        out = torch.empty(csr.n_rows, x.size(1), dtype=x.dtype, device=x.device)
+        accumulate = False
+    if csr.n_rows:
+        _lib.check(lib.trg_gather_wsum(_lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(csr.eid),
+                                       _lib.ptr(coef), _lib.ptr(scale), _lib.ptr(x), csr.n_rows,
+                                       x.size(1), _lib.dtype_code(x.dtype), _lib.ptr(out),
+                                       1 if accumulate else 0, _lib.stream()),
+                   "trg_gather_wsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# K4: link-prediction loss (train_gnn.py:259-281) and its backward
+# ------------------------------------------------------------------------------------------
+class LinkStructure:
+    """Static structures of the positive edge set: edges grouped by user and by post, and
+    wbar = mean(interaction_type_tensor[pos_p + num_users]) (train_gnn.py:266-269,280)."""
+
+    def __init__(self, train_edge_index, interaction_type_tensor, num_users, num_posts):
+        pos_u, pos_p = train_edge_index[0], train_edge_index[1]
+        self.train_edge_index = train_edge_index
+        self.num_users, self.num_posts = int(num_users), int(num_posts)
+        self.n_edges = int(pos_u.numel())
+        self.by_user = build_csr(pos_p, pos_u, self.num_users, self.num_posts)
+        self.by_post = build_csr(pos_u, pos_p, self.num_posts, self.num_users, validate=False)
+        if self.n_edges:
+            w = interaction_type_tensor[pos_p + num_users].float()
+            self.wbar = w.mean().reshape(1).contiguous()
+        else:
+            self.wbar = torch.full((1,), float("nan"), device=pos_u.device)
+
+
+_LINK_CACHE: dict = {}
+
+
+def link_structure(train_edge_index, interaction_type_tensor, num_users, num_posts) -> LinkStructure:
+    key = (train_edge_index.data_ptr(), tuple(train_edge_index.shape), train_edge_index._version,
+           interaction_type_tensor.data_ptr(), interaction_type_tensor._version, int(num_users),
+           int(num_posts))
+    s = _LINK_CACHE.get(key)
+    if s is None:
+        if len(_LINK_CACHE) > 8:
+            _LINK_CACHE.clear()
+        s = LinkStructure(train_edge_index, interaction_type_tensor, num_users, num_posts)
+        s._keepalive = interaction_type_tensor
+        _LINK_CACHE[key] = s
+    return s
+
+
+def edge_bce_fwd(ls: LinkStructure, user_emb, post_emb, neg_p, want_grad: bool):
+    lib = _lib.load()
+    _check_rows(user_emb, "edge_bce_fwd")
+    if user_emb.dtype != post_emb.dtype or user_emb.size(1) != post_emb.size(1):
+        raise _lib.TrgError("user and post embeddings must share dtype and width")
+    if neg_p.dtype != torch.int64 or neg_p.numel() != ls.n_edges:
+        raise _lib.TrgError("neg_p must be int64 with one entry per positive edge (train_gnn.py:272)")
+    user_emb, post_emb, neg_p = user_emb.contiguous(), post_emb.contiguous(), neg_p.contiguous()
+    dev = user_emb.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    c_pos = c_neg = g_u = None
+    if want_grad:
+        c_pos = torch.empty(ls.n_edges, dtype=torch.float32, device=dev)
+        c_neg = torch.empty(ls.n_edges, dtype=torch.float32, device=dev)
+        g_u = torch.empty_like(user_emb)
+    ws_bytes = int(lib.trg_edge_bce_workspace_bytes(ls.num_users))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    e = ls.n_edges
+    _lib.check(lib.trg_edge_bce_fwd(_lib.ptr(ls.by_user.rowptr), _lib.ptr(ls.by_user.col) if e else None,
+                                    _lib.ptr(ls.by_user.eid) if e else None, _lib.ptr(neg_p) if e else None,
+                                    _lib.ptr(user_emb), _lib.ptr(post_emb), ls.num_users, e,
+                                    user_emb.size(1), _lib.dtype_code(user_emb.dtype), _lib.ptr(ls.wbar),
+                                    _lib.ptr(loss), _lib.ptr(c_pos), _lib.ptr(c_neg), _lib.ptr(g_u),
+                                    _lib.ptr(ws), ws_bytes, _lib.stream()),
+               "trg_edge_bce_fwd")
+    return loss, c_pos, c_neg, g_u
+
+
+class LinkBCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, user_emb, post_emb, neg_p, ls: LinkStructure):
+        want = user_emb.requires_grad or post_emb.requires_grad
+        loss, c_pos, c_neg, g_u = edge_bce_fwd(ls, user_emb, post_emb, neg_p, want)
+        ctx.ls = ls
+        ctx.want = want
+        if want:
+            ctx.save_for_backward(user_emb, neg_p, c_pos, c_neg, g_u)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        user_emb, neg_p, c_pos, c_neg, g_u = ctx.saved_tensors
+        ls = ctx.ls
+        g = g.reshape(1).float().contiguous()
+        g_user = g_post = None
+        if ctx.needs_input_grad[0]:
+            g_user = g_u * g.to(g_u.dtype)
+        if ctx.needs_input_grad[1]:
+            pos_u = ls.train_edge_index[0]
+            # dloss/dp = sum over positive edges of the post (static structure) ...
+            g_post = gather_wsum(ls.by_post, c_pos, user_emb, scale=g)
+            # ... plus the sampled negatives, grouped by post with this step's stable sort
+            neg_csr = build_csr(pos_u, neg_p, ls.num_posts, ls.num_users, validate=False)
+            gather_wsum(neg_csr, c_neg, user_emb, scale=g, out=g_post, accumulate=True)
+        return g_user, g_post, None, None
+
+
+def link_bce_loss(user_emb, post_emb, train_edge_index, neg_p, interaction_type_tensor, num_users):
+    """``loss`` of train_gnn.py:259-281 given this step's negatives (``torch.randint`` at :272)."""
+    ls = link_structure(train_edge_index, interaction_type_tensor, num_users, post_emb.size(0))
+    return LinkBCEFn.apply(user_emb, post_emb, neg_p, ls)
+
+
+# ------------------------------------------------------------------------------------------
+# K3: projections + combine + ReLU
+# ------------------------------------------------------------------------------------------
+def sage_proj_fwd(terms, bias, relu: bool):
+    """``out = act(sum_i alpha_i * A_i @ W_i^T + bias)``; terms = [(A, W, alpha), ...]."""
+    lib = _lib.load()
+    a0 = terms[0][0]
+    n, hidden = a0.size(0), terms[0][1].size(0)
+    arr = (_lib.TrgProjTerm * len(terms))()
+    keep = []
+    for i, (a, w, alpha) in enumerate(terms):
+        a, w = a.contiguous(), w.contiguous()
+        if a.dtype != a0.dtype or w.dtype != a0.dtype:
+            raise _lib.TrgError("projection operands must share one dtype")
+        keep += [a, w]
+        arr[i].a, arr[i].w, arr[i].k, arr[i].alpha = _lib.ptr(a), _lib.ptr(w), a.size(1), float(alpha)
+    out = torch.empty(n, hidden, dtype=a0.dtype, device=a0.device)
+    b = bias.float().contiguous() if bias is not None else None
+    _lib.check(lib.trg_sage_proj_fwd(arr, len(terms), _lib.ptr(b), n, hidden, _lib.dtype_code(a0.dtype),
+                                     1 if relu else 0, _lib.ptr(out), _lib.stream()),
+               "trg_sage_proj_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# K5: score contraction + top-k (inference.py:427-428)
+# ------------------------------------------------------------------------------------------
+def score_topk(q: torch.Tensor, cat: torch.Tensor, k: int, id_offset: int = 0):
+    """``torch.topk(torch.mm(q, cat.T), min(k, len))`` without materialising the scores.
+    Returns ``(values[B,k'] fp32 descending, ids[B,k'] int64)`` under (score desc, id asc)."""
+    lib = _lib.load()
+    if q.dim() == 1:
+        q = q.unsqueeze(0)
+    q, cat = q.contiguous(), cat.contiguous()
+    b, h = q.shape
+    p = cat.size(0)
+    kk = min(int(k), p)
+    vals = torch.empty(b, kk, dtype=torch.float32, device=q.device)
+    ids = torch.empty(b, kk, dtype=torch.int64, device=q.device)
+    if b == 0 or kk == 0:
+        return vals, ids
+    ws_bytes = int(lib.trg_score_topk_workspace_bytes(b, p, h, kk))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    _lib.check(lib.trg_score_topk(_lib.ptr(q), _lib.ptr(cat), b, p, h, _lib.dtype_code(q.dtype), kk,
+                                  int(id_offset), _lib.ptr(vals), _lib.ptr(ids), _lib.ptr(ws), ws_bytes,
+                                  _lib.stream()),
+               "trg_score_topk")
+    return vals, ids
+
+
+def topk_merge(vals_in: torch.Tensor, ids_in: torch.Tensor, n_lists: int, k_out: int):
+    lib = _lib.load()
+    b = vals_in.size(0)
+    k_in = vals_in.size(1) // n_lists
+    vals = torch.empty(b, k_out, dtype=torch.float32, device=vals_in.device)
+    ids = torch.empty(b, k_out, dtype=torch.int64, device=vals_in.device)
+    _lib.check(lib.trg_topk_merge(_lib.ptr(vals_in.contiguous()), _lib.ptr(ids_in.contiguous()), b,
+                                  n_lists, k_in, k_out, _lib.ptr(vals), _lib.ptr(ids), _lib.stream()),
+               "trg_topk_merge")
+    return vals, ids

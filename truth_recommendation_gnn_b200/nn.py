@@ -1,0 +1,168 @@
+"""Drop-in modules for the reference's model-construction API.
+
+``SAGEConv`` mirrors ``torch_geometric.nn.SAGEConv`` for exactly the options the reference relies
+on (train_gnn.py:158-160: ``aggr='mean'``, ``root_weight=True``, ``bias=True``,
+``normalize=False``, ``project=False``) with the same constructor, call signature and
+``state_dict`` keys (``lin_l.weight``, ``lin_l.bias``, ``lin_r.weight``), so
+``from truth_recommendation_gnn_b200.nn import SAGEConv`` replaces
+``from torch_geometric.nn import SAGEConv`` (train_gnn.py:6, inference.py:117) and the scripts'
+``WeightedRGCN`` class, optimizer construction, checkpointing and ``load_state_dict`` keep working
+unchanged.  ``WeightedRGCN`` here is the same model with the projections, relation combine and
+ReLU fused.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch.nn.parameter import Parameter, UninitializedParameter
+
+from . import _lib
+from .functional import sage_mean_aggregate
+from .graph import relation_graph
+
+REL_DIRECT = ("post", "rev_engages", "user")
+REL_SOCIAL = ("user", "social", "user")
+REL_ENGAGE = ("user", "engages", "post")
+
+
+class Linear(torch.nn.Module):
+    """``torch_geometric.nn.dense.linear.Linear`` semantics: ``in_channels = -1`` is resolved at the
+    first forward or by ``load_state_dict`` IN PLACE (the optimizer built at train_gnn.py:207
+    already holds the Parameter objects).  Default init = ``torch.nn.Linear``'s."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        if in_channels > 0:
+            self.weight = Parameter(torch.empty(out_channels, in_channels))
+        else:
+            self.weight = UninitializedParameter()
+        if bias:
+            self.bias = Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.in_channels <= 0:
+            return
+        torch.nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1.0 / math.sqrt(self.in_channels)
+            torch.nn.init.uniform_(self.bias, -bound, bound)
+
+    def materialize(self, in_channels: int):
+        if isinstance(self.weight, UninitializedParameter):
+            self.in_channels = int(in_channels)
+            self.weight.materialize((self.out_channels, self.in_channels))
+            self.reset_parameters()
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        if isinstance(self.weight, UninitializedParameter):
+            destination[prefix + "weight"] = self.weight  # like PyG: lazy weights stay placeholders
+            if self.bias is not None:
+                destination[prefix + "bias"] = self.bias if keep_vars else self.bias.detach()
+        else:
+            super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                              unexpected_keys, error_msgs):
+        w = state_dict.get(prefix + "weight")
+        if w is not None and isinstance(self.weight, UninitializedParameter):
+            self.in_channels = int(w.size(-1))
+            self.weight.materialize(tuple(w.shape))
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
+                                      unexpected_keys, error_msgs)
+
+    def forward(self, x):
+        self.materialize(x.size(-1))
+        return F.linear(x, self.weight, self.bias)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, bias={self.bias is not None}"
+
+
+class SAGEConv(torch.nn.Module):
+    r"""``out = lin_l(mean_{j in N(i)} x_j) + lin_r(x_i)`` -- replaces PyG's operator at
+    train_gnn.py:158-160 (ctor) and :177-184,194-197 (calls).
+
+    ``forward((x_src, x_dst), edge_index)`` with bipartite ``edge_index[2,E]`` int64
+    (``edge_index[0]`` in ``[0, N_src)``, ``edge_index[1]`` in ``[0, N_dst)``); a single tensor
+    ``x`` means ``(x, x)``.  E = 0 and N_src = 0 are valid (inference.py:412-419).
+    """
+
+    def __init__(self, in_channels, out_channels: int, aggr: str = "mean", normalize: bool = False,
+                 root_weight: bool = True, project: bool = False, bias: bool = True):
+        super().__init__()
+        if aggr != "mean" or normalize or project or not root_weight:
+            raise NotImplementedError(
+                "only the configuration the reference uses is accelerated: aggr='mean', "
+                "normalize=False, root_weight=True, project=False (train_gnn.py:158-160)")
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        self.in_channels, self.out_channels = tuple(in_channels), out_channels
+        self.lin_l = Linear(in_channels[0], out_channels, bias=bias)
+        self.lin_r = Linear(in_channels[1], out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def aggregate(self, x_src, edge_index, n_dst):
+        """K0 (cached) + K1: mean of in-neighbour rows."""
+        rel = relation_graph(edge_index, x_src.size(0), n_dst)
+        return sage_mean_aggregate(x_src, rel)
+
+    def forward(self, x, edge_index, size=None):
+        if isinstance(x, torch.Tensor):
+            x = (x, x)
+        x_src, x_dst = x
+        if not x_dst.is_cuda:
+            raise _lib.TrgError("SAGEConv (B200) needs CUDA tensors; there is no CPU fallback")
+        self.lin_l.materialize(x_src.size(-1))
+        self.lin_r.materialize(x_dst.size(-1))
+        mean = self.aggregate(x_src, edge_index, x_dst.size(0))
+        return self.lin_l(mean) + self.lin_r(x_dst)
+
+    def __repr__(self):
+        return f"SAGEConv({self.in_channels}, {self.out_channels}, aggr=mean)"
+
+
+class WeightedRGCN(torch.nn.Module):
+    """The reference model, train_gnn.py:147-200 (dup inference.py:119-169): same attribute names,
+    same fixed python-float relation weights, same ``forward(x_dict, edge_index_dict)``."""
+
+    def __init__(self, hidden_dim=64, in_channels=(-1, -1)):
+        super().__init__()
+        self.msg_direct = SAGEConv(in_channels, hidden_dim)   # user <- post (engagement)
+        self.msg_social = SAGEConv(in_channels, hidden_dim)   # user <- user (social)
+        self.post_update = SAGEConv(in_channels, hidden_dim)  # post <- user (engagement)
+        self.w_direct = 1.0
+        self.w_social = 0.75
+
+    def forward(self, x_dict, edge_index_dict):
+        user_x, post_x = x_dict["user"], x_dict["post"]
+        msg_direct = self.msg_direct((post_x, user_x), edge_index_dict[REL_DIRECT])
+        msg_social = self.msg_social((user_x, user_x), edge_index_dict[REL_SOCIAL])
+        user_out = F.relu(self.w_direct * msg_direct + self.w_social * msg_social)
+        post_out = F.relu(self.post_update((user_x, post_x), edge_index_dict[REL_ENGAGE]))
+        return {"user": user_out, "post": post_out}
+
+
+class StackedWeightedRGCN(torch.nn.Module):
+    """L stacked ``WeightedRGCN`` blocks (BASELINE.json configs 1-4 ask for 2-3 layers; the
+    reference has one).  Stacking rule of SURVEY.md §8: layer l has its own three convs, is fed
+    the ``{'user','post'}`` output of layer l-1, and ReLU follows every layer."""
+
+    def __init__(self, hidden_dim=64, num_layers=2, in_channels=(-1, -1)):
+        super().__init__()
+        self.layers = torch.nn.ModuleList(
+            [WeightedRGCN(hidden_dim, in_channels if i == 0 else (hidden_dim, hidden_dim))
+             for i in range(num_layers)])
+
+    def forward(self, x_dict, edge_index_dict):
+        for layer in self.layers:
+            x_dict = layer(x_dict, edge_index_dict)
+        return x_dict

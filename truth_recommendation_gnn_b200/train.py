@@ -1,0 +1,35 @@
+"""The reference's training step and recommendation call, on the B200 kernels.
+
+``train_step`` is the body of ``train()`` (train_gnn.py:242-285) with the same order of
+operations: zero_grad -> forward -> positive/negative scoring -> loss -> backward -> Adam step.
+``recommend`` is inference.py:427-428.
+"""
+from __future__ import annotations
+
+import torch
+
+from .functional import link_bce_loss, score_topk
+
+
+def train_step(model, optimizer, x_dict, edge_index_dict, train_edge_index, interaction_type_tensor,
+               num_users, num_posts, neg_p=None, return_tensor=False):
+    """One full-batch step.  ``neg_p`` defaults to ``torch.randint(0, num_posts, (E,), device)`` as
+    at train_gnn.py:272.  Returns ``loss.item()`` (train_gnn.py:285) or the 0-d device tensor when
+    ``return_tensor`` (no host sync)."""
+    model.train()
+    optimizer.zero_grad()
+    out = model(x_dict, edge_index_dict)
+    user_emb, post_emb = out["user"], out["post"]
+    if neg_p is None:
+        neg_p = torch.randint(0, num_posts, (train_edge_index.size(1),), device=user_emb.device)
+    loss = link_bce_loss(user_emb, post_emb, train_edge_index, neg_p, interaction_type_tensor, num_users)
+    loss.backward()
+    optimizer.step()
+    return loss.detach() if return_tensor else loss.item()
+
+
+@torch.no_grad()
+def recommend(user_emb, known_post_emb, k=10, id_offset=0):
+    """``scores = torch.mm(user_emb, known_post_emb.T); torch.topk(scores, min(K, len(scores)))``
+    (inference.py:427-428) for one user row or a batch.  Returns ``(top scores, top post ids)``."""
+    return score_topk(user_emb, known_post_emb, k, id_offset)
