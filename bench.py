@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the hetero-SAGE hot path (BASELINE.json metric: message-passing edges/s over one
+train step, plus top-k recs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2]
+
+A "step" is the body of the reference's ``train()`` (train_gnn.py:242-285): zero_grad -> forward
+-> pos/neg scoring + loss -> backward -> Adam step, full batch.  ``value`` = L * (2*E_eng + E_soc)
+/ t_step with everything resident in HBM; ``e2e`` = the same through the public API with this
+step's host inputs (the sampled negatives, pinned host memory) copied in and the loss read back
+inside the timed region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "message-passing edges/s (train step)"
+UNIT = "edges/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (fits one GPU)
+    "cfg2": dict(num_users=1_000_000, num_posts=5_000_000, e_eng=40_000_000, e_soc=10_000_000,
+                 hidden=128, layers=2, dtype="f32"),
+    # configs[2]: same graph in bf16 (multi-GPU scaling config)
+    "cfg3": dict(num_users=1_000_000, num_posts=5_000_000, e_eng=40_000_000, e_soc=10_000_000,
+                 hidden=128, layers=2, dtype="bf16"),
+    # configs[0]: the reference's own CPU-runnable scale
+    "cfg1": dict(num_users=10_000, num_posts=50_000, e_eng=400_000, e_soc=100_000,
+                 hidden=64, layers=2, dtype="f32"),
+    "tiny": dict(num_users=2_000, num_posts=8_000, e_eng=60_000, e_soc=15_000,
+                 hidden=64, layers=2, dtype="f32"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def step_bytes(w, elem):
+    """Algorithmic HBM bytes of one train step."""
+    U, P, Ee, Es, H, L = w["num_users"], w["num_posts"], w["e_eng"], w["e_soc"], w["hidden"], w["layers"]
+    F, s = H, elem
+    rels = [(Ee, P, U), (Es, U, U), (Ee, U, P)]          # (E, N_src, N_dst)
+    A = sum(e * (F * s + 4) + 4 * (nd + 1) + nd * F * s for e, ns, nd in rels)
+    B = U * (3 * F * s + H * s) + P * (2 * F * s + H * s)
+    C = Ee * (3 * H * s + 12)
+    D = Ee * (3 * H * s + 12) + (U + P) * H * s
+    G = sum(e * (F * s + 4) + 4 * (ns + 1) + ns * F * s + 4 * nd for e, ns, nd in rels)
+    return L * (A + B + B) + C + D + (L - 1) * (B + G)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons, pw = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median over the busiest half (samples under load)
+        busy = sorted(sm, key=lambda x: x)[len(sm) // 2:] if len(sm) > 3 else sm
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "sm_mhz_busy_median": statistics.median(busy)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference path; PyG itself is not installable) on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_workload(w):
+    """Bounded sample of the workload: same H / L / edge mix, graph scaled so that one oracle step
+    is a few seconds of CPU work."""
+    scale = 50 if w["num_users"] >= 1_000_000 else 1
+    s = dict(w)
+    for k in ("num_users", "num_posts", "e_eng", "e_soc"):
+        s[k] = max(w[k] // scale, 1)
+    desc = (f"{'1/%d-scale ' % scale if scale > 1 else ''}graph {s['num_users']} users / {s['num_posts']} posts / "
+            f"{s['e_eng'] + s['e_soc']} edges, H={s['hidden']}, L={s['layers']}, fp32, full train step "
+            f"(CPU oracle: pure-torch restatement of PyG SAGEConv; torch_geometric is not installable)")
+    return s, desc
+
+
+def run_cpu_oracle(w, steps, warmup):
+    from oracle import sage as osage   # the one place bench.py executes oracle/: the CPU baseline
+    from truth_recommendation_gnn_b200 import synth
+    s, desc = cpu_sample_workload(w)
+    g = synth.synth_graph(s["num_users"], s["num_posts"], s["e_eng"], s["e_soc"], s["hidden"], seed=0)
+    H, L = s["hidden"], s["layers"]
+    model = (osage.WeightedRGCNOracle(H, (H, H)) if L == 1 else osage.StackedWeightedRGCNOracle(H, L, (H, H)))
+    model.load_state_dict(synth.init_state_dict(H, H, L))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    times = []
+    for i in range(warmup + steps):
+        neg = synth.synth_neg(s["num_posts"], s["e_eng"], i)
+        t0 = time.perf_counter()
+        osage.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
+                         g.interaction_type_tensor, s["num_users"], s["num_posts"], neg_p=neg)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    mp = L * (2 * s["e_eng"] + s["e_soc"])
+    return dict(value=mp / t, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=desc,
+                ms_per_step=t * 1e3, host_cpus=os.cpu_count())
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    cb = run_cpu_oracle(w, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, **{k: w[k] for k in ("num_users", "num_posts", "e_eng", "e_soc", "hidden", "layers")},
+                   "note": "CPU arm runs a bounded sample of this workload, see cpu_baseline.sample"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_train_bench(args, w, rank, world, dev):
+    import truth_recommendation_gnn_b200 as trg
+    from truth_recommendation_gnn_b200 import _lib, synth
+
+    dtype = torch.float32 if w["dtype"] == "f32" else torch.bfloat16
+    U, P, Ee, Es, H, L = w["num_users"], w["num_posts"], w["e_eng"], w["e_soc"], w["hidden"], w["layers"]
+    t_setup0 = time.perf_counter()
+    g = synth.synth_graph(U, P, Ee, Es, H, seed=0, device=dev, dtype=dtype)
+    model = trg.WeightedRGCN(H) if L == 1 else trg.StackedWeightedRGCN(H, L)
+    model.load_state_dict(synth.init_state_dict(H, H, L))
+    model = model.to(dev).to(dtype)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    # this step's host input: the sampled negatives (train_gnn.py:272), pinned
+    n_host = 4
+    neg_host = [synth.synth_neg(P, Ee, i).pin_memory() for i in range(n_host)]
+    neg_dev = [t.to(dev) for t in neg_host]
+    torch.cuda.synchronize()
+
+    def step(i, e2e):
+        if e2e:
+            neg = neg_host[i % n_host].to(dev, non_blocking=True)
+            return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
+                                  g.interaction_type_tensor, U, P, neg_p=neg)          # loss.item(): D2H
+        return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
+                              g.interaction_type_tensor, U, P, neg_p=neg_dev[i % n_host], return_tensor=True)
+
+    for i in range(args.warmup):
+        step(i, False)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup0
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    # ---- timed region 1: resident inputs (value) ----
+    clocks = ClockSampler(dev.index or 0)
+    _lib.PROF.reset()
+    _lib.PROF.enabled = True
+    barrier(); torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i, False)
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    clk = clocks.stop()
+    n1 = _lib.launch_count()
+    _lib.PROF.enabled = False
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = _lib.PROF.summary()
+
+    # ---- timed region 2: end to end through the public API with host buffers ----
+    for i in range(2):
+        step(i, True)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(i, True)
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    mp_edges = L * (2 * Ee + Es)
+    return dict(ms=ms, ms_e2e=ms_e2e, mp_edges=mp_edges, prof=prof, launches=(n1 - n0), clocks=clk,
+                setup_s=setup_s, h2d=Ee * 8, d2h=4, mem_gb=torch.cuda.max_memory_allocated(dev) / 2**30)
+
+
+def gpu_topk_bench(args, dev, n_post, hidden, k=100, batch=4096, iters=3):
+    """Secondary metric: top-k recs/s (inference.py:427-428 batched; BASELINE config 5 shape)."""
+    import truth_recommendation_gnn_b200 as trg
+    from truth_recommendation_gnn_b200 import synth
+    q, cat = synth.synth_queries(batch, n_post, hidden, device=dev)
+    trg.score_topk(q, cat, k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        trg.score_topk(q, cat, k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return dict(users_per_s=batch / ms * 1e3, recs_per_s=batch * k / ms * 1e3, ms_per_batch=ms,
+                tflops=2.0 * batch * n_post * hidden / ms / 1e9, batch=batch, n_post=n_post, hidden=hidden, k=k,
+                dtype="f32", kernel="score_topk_f32 (SIMT fp32 FMA)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-topk", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "cfg2" if world == 1 else "cfg3"
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=b200) needs a CUDA device: the hot path has no CPU fallback")
+    args.warmup = max(args.warmup, 3)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    if world > 1:
+        from truth_recommendation_gnn_b200 import dist as tdist
+        r = tdist.bench_train(args, w, rank, world, dev)
+    else:
+        r = gpu_train_bench(args, w, rank, world, dev)
+
+    if rank == 0:
+        pk = peaks()
+        elem = 4 if w["dtype"] == "f32" else 2
+        value = r["mp_edges"] / r["ms"] * 1e3
+        gat = [r["prof"].get(n) for n in ("trg_sage_agg_fwd", "trg_sage_agg_bwd", "trg_gather_wsum")]
+        gat = [d for d in gat if d]
+        g_bytes, g_ms, g_calls = (sum(d["bytes"] for d in gat), sum(d["ms"] for d in gat), sum(d["calls"] for d in gat))
+        achieved = g_bytes / g_ms / 1e6 if g_ms > 0 else 0.0            # GB/s
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gather_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        sb = step_bytes(w, elem)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['num_users']} users / {w['num_posts']} posts / "
+                                   f"{w['e_eng'] + w['e_soc']} edges, {w['layers']}-layer hetero SAGE hidden={w['hidden']} "
+                                   f"{w['dtype']}, one full-batch link-pred train step (fwd+loss+bwd+Adam)",
+                       "mp_edges_per_step": r["mp_edges"], "l2": "inputs exceed L2 (tables >= 0.5 GB, L2 = 126 MB)",
+                       "parallelism": "single GPU" if world == 1 else f"dst-partitioned x{world}, all-gather per layer"},
+            "e2e": {"value": r["mp_edges"] / r["ms_e2e"] * 1e3, "unit": UNIT, "ms_per_step": r["ms_e2e"],
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "what": "train_step() via the public API; per step the sampled negatives (int64[E_eng]) are "
+                            "copied from pinned host memory and loss.item() is read back; graph + features stay "
+                            "resident as in the reference (graph.to(device) once, train_gnn.py:211)"},
+            "gpu_launches": r["launches"],
+            "clocks": r["clocks"],
+            "roofline": {"bound": "hbm", "kernel": "gather_reduce (trg_sage_agg_fwd/bwd, trg_gather_wsum)",
+                         "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
+                         "launches": g_calls, "avg_ms_per_launch": g_ms / max(g_calls, 1),
+                         "algorithmic_bytes_per_launch": g_bytes / max(g_calls, 1),
+                         "share_of_step": g_ms / (r["ms"] * args.steps)},
+            "step_roofline": {"algorithmic_bytes_per_step": sb, "achieved_gbs": sb / r["ms"] / 1e6,
+                              "frac": sb / r["ms"] / 1e6 / pk["hbm_gbs"], "roofline_ms": sb / pk["hbm_gbs"] / 1e6},
+            "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(r["prof"].items())},
+            "kernels_gbs": {k: round(v["bytes"] / v["ms"] / 1e6, 1) for k, v in sorted(r["prof"].items()) if v["ms"] > 0},
+            "setup_s": round(r["setup_s"], 2), "peak_mem_gb": round(r["mem_gb"], 2),
+        }
+        if not args.no_topk and world == 1:
+            npost = w["num_posts"] if w["num_posts"] <= 5_000_000 else 5_000_000
+            line["topk"] = gpu_topk_bench(args, dev, npost, w["hidden"], k=100, batch=4096)
+        if not args.no_cpu_baseline and world == 1:
+            cb = run_cpu_oracle(w, 3, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,5 +95,43 @@ def dtype_code(dt: torch.dtype) -> int:
     raise TrgError(f"unsupported dtype {dt}: the hot path computes in fp32 or bf16 (fp32 accumulate)")
 
 
+class Profiler:
+    """Optional per-call CUDA-event timing of the C-ABI launches (used by bench.py to measure the
+    dominant kernel live, on the launching stream).  Disabled by default: zero overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []   # (name, algorithmic_bytes, start_event, end_event)
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        """name -> dict(calls, ms, bytes); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, nbytes, s, e in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, bytes=0))
+            d["calls"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["bytes"] += int(nbytes)
+        return out
+
+
+PROF = Profiler()
+
+
+def call(name, nbytes, fn, *args):
+    """Invoke a C-ABI function, check its return code, optionally time it with CUDA events."""
+    if PROF.enabled:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        PROF.records.append((name, nbytes, s, e))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+
+
 def launch_count() -> int:
     return int(load().trg_launch_count())

@@ -31,10 +31,11 @@ def sage_agg_fwd(csr: CSR, x_src: torch.Tensor, want_inv_deg: bool = True):
     out = torch.empty(csr.n_rows, x_src.size(1), dtype=x_src.dtype, device=x_src.device)
     inv_deg = torch.empty(csr.n_rows, dtype=torch.float32, device=x_src.device) if want_inv_deg else None
     if csr.n_rows:
-        _lib.check(lib.trg_sage_agg_fwd(_lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(x_src),
-                                        csr.n_rows, x_src.size(1), _lib.dtype_code(x_src.dtype),
-                                        _lib.ptr(out), _lib.ptr(inv_deg), _lib.stream()),
-                   "trg_sage_agg_fwd")
+        rb = x_src.size(1) * x_src.element_size()
+        nbytes = csr.n_edges * (rb + 4) + 4 * (csr.n_rows + 1) + csr.n_rows * rb
+        _lib.call("trg_sage_agg_fwd", nbytes, lib.trg_sage_agg_fwd,
+                  _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(x_src), csr.n_rows, x_src.size(1),
+                  _lib.dtype_code(x_src.dtype), _lib.ptr(out), _lib.ptr(inv_deg), _lib.stream())
     return out, inv_deg
 
 
@@ -45,10 +46,12 @@ def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor):
     _check_rows(g_mean, "sage_agg_bwd")
     out = torch.empty(csr_t.n_rows, g_mean.size(1), dtype=g_mean.dtype, device=g_mean.device)
     if csr_t.n_rows:
-        _lib.check(lib.trg_sage_agg_bwd(_lib.ptr(csr_t.rowptr), _lib.ptr(csr_t.col), _lib.ptr(inv_deg),
-                                        _lib.ptr(g_mean), csr_t.n_rows, g_mean.size(1),
-                                        _lib.dtype_code(g_mean.dtype), _lib.ptr(out), _lib.stream()),
-                   "trg_sage_agg_bwd")
+        rb = g_mean.size(1) * g_mean.element_size()
+        nbytes = (csr_t.n_edges * (rb + 4) + 4 * (csr_t.n_rows + 1) + csr_t.n_rows * rb
+                  + 4 * csr_t.n_cols)
+        _lib.call("trg_sage_agg_bwd", nbytes, lib.trg_sage_agg_bwd,
+                  _lib.ptr(csr_t.rowptr), _lib.ptr(csr_t.col), _lib.ptr(inv_deg), _lib.ptr(g_mean),
+                  csr_t.n_rows, g_mean.size(1), _lib.dtype_code(g_mean.dtype), _lib.ptr(out), _lib.stream())
     return out
 
 
@@ -83,11 +86,13 @@ def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulat
         out = torch.empty(csr.n_rows, x.size(1), dtype=x.dtype, device=x.device)
         accumulate = False
     if csr.n_rows:
-        _lib.check(lib.trg_gather_wsum(_lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(csr.eid),
-                                       _lib.ptr(coef), _lib.ptr(scale), _lib.ptr(x), csr.n_rows,
-                                       x.size(1), _lib.dtype_code(x.dtype), _lib.ptr(out),
-                                       1 if accumulate else 0, _lib.stream()),
-                   "trg_gather_wsum")
+        rb = x.size(1) * x.element_size()
+        nbytes = (csr.n_edges * (rb + 12) + 4 * (csr.n_rows + 1)
+                  + csr.n_rows * rb * (2 if accumulate else 1))
+        _lib.call("trg_gather_wsum", nbytes, lib.trg_gather_wsum,
+                  _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(csr.eid), _lib.ptr(coef),
+                  _lib.ptr(scale), _lib.ptr(x), csr.n_rows, x.size(1), _lib.dtype_code(x.dtype),
+                  _lib.ptr(out), 1 if accumulate else 0, _lib.stream())
     return out
 
 
@@ -147,13 +152,14 @@ def edge_bce_fwd(ls: LinkStructure, user_emb, post_emb, neg_p, want_grad: bool):
     ws_bytes = int(lib.trg_edge_bce_workspace_bytes(ls.num_users))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     e = ls.n_edges
-    _lib.check(lib.trg_edge_bce_fwd(_lib.ptr(ls.by_user.rowptr), _lib.ptr(ls.by_user.col) if e else None,
-                                    _lib.ptr(ls.by_user.eid) if e else None, _lib.ptr(neg_p) if e else None,
-                                    _lib.ptr(user_emb), _lib.ptr(post_emb), ls.num_users, e,
-                                    user_emb.size(1), _lib.dtype_code(user_emb.dtype), _lib.ptr(ls.wbar),
-                                    _lib.ptr(loss), _lib.ptr(c_pos), _lib.ptr(c_neg), _lib.ptr(g_u),
-                                    _lib.ptr(ws), ws_bytes, _lib.stream()),
-               "trg_edge_bce_fwd")
+    rb = user_emb.size(1) * user_emb.element_size()
+    nbytes = e * (2 * rb + 16 + (8 if want_grad else 0)) + ls.num_users * (rb * (2 if want_grad else 1) + 4)
+    _lib.call("trg_edge_bce_fwd", nbytes, lib.trg_edge_bce_fwd,
+              _lib.ptr(ls.by_user.rowptr), _lib.ptr(ls.by_user.col) if e else None,
+              _lib.ptr(ls.by_user.eid) if e else None, _lib.ptr(neg_p) if e else None,
+              _lib.ptr(user_emb), _lib.ptr(post_emb), ls.num_users, e, user_emb.size(1),
+              _lib.dtype_code(user_emb.dtype), _lib.ptr(ls.wbar), _lib.ptr(loss), _lib.ptr(c_pos),
+              _lib.ptr(c_neg), _lib.ptr(g_u), _lib.ptr(ws), ws_bytes, _lib.stream())
     return loss, c_pos, c_neg, g_u
 
 
@@ -235,10 +241,9 @@ def score_topk(q: torch.Tensor, cat: torch.Tensor, k: int, id_offset: int = 0):
         return vals, ids
     ws_bytes = int(lib.trg_score_topk_workspace_bytes(b, p, h, kk))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
-    _lib.check(lib.trg_score_topk(_lib.ptr(q), _lib.ptr(cat), b, p, h, _lib.dtype_code(q.dtype), kk,
-                                  int(id_offset), _lib.ptr(vals), _lib.ptr(ids), _lib.ptr(ws), ws_bytes,
-                                  _lib.stream()),
-               "trg_score_topk")
+    _lib.call("trg_score_topk", 2 * b * p * h, lib.trg_score_topk,  # "bytes" slot carries flops here
+              _lib.ptr(q), _lib.ptr(cat), b, p, h, _lib.dtype_code(q.dtype), kk, int(id_offset),
+              _lib.ptr(vals), _lib.ptr(ids), _lib.ptr(ws), ws_bytes, _lib.stream())
     return vals, ids
 
 

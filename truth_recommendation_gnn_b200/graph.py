@@ -52,10 +52,10 @@ def build_csr(other: torch.Tensor, key: torch.Tensor, n_key: int, n_other: int,
     eid = torch.empty(e, dtype=torch.int32, device=dev)
     ws_bytes = int(lib.trg_csr_workspace_bytes(e, n_key))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.trg_csr_build(_lib.ptr(other) if e else None, _lib.ptr(key) if e else None, e, n_key,
-                                 _lib.ptr(rowptr), _lib.ptr(col) if e else None,
-                                 _lib.ptr(eid) if e else None, _lib.ptr(ws), ws_bytes, _lib.stream()),
-               "trg_csr_build")
+    _lib.call("trg_csr_build", e * 80 + 8 * (n_key + 1), lib.trg_csr_build,
+              _lib.ptr(other) if e else None, _lib.ptr(key) if e else None, e, n_key, _lib.ptr(rowptr),
+              _lib.ptr(col) if e else None, _lib.ptr(eid) if e else None, _lib.ptr(ws), ws_bytes,
+              _lib.stream())
     return CSR(rowptr, col, eid, n_key, n_other)
 
 
