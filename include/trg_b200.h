@@ -102,19 +102,37 @@ int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, const int32_
 /* ---- A3+A4 / K3: SAGE projections + relation combine + ReLU ---------------------------------
  * Replaces lin_l(mean) + lin_r(x_dst) of every SAGEConv and the combine of
  * train_gnn.py:187-198.  out = act( sum_i alpha_i * ( A_i[n, k_i] @ W_i[h, k_i]^T ) + bias ),
- * up to 4 (A, W) pairs (user rows: mean_direct, x, mean_social, x; post rows: mean, x).
+ * up to 4 (A, W) pairs (user rows: mean_direct, mean_social, x; post rows: mean, x).
  * fp32 inputs are multiplied as 3xTF32 split products on tcgen05 (fp32-accurate), bf16 inputs as
- * kind::f16 with fp32 TMEM accumulation. */
+ * kind::f16 with fp32 TMEM accumulation (hidden in {64,128,256}, k_i a multiple of 128 bytes);
+ * other shapes take a strict-fp32 FMA kernel.  Workspace: trg_sage_proj_workspace_bytes. */
 typedef struct {
   const void* a;      /* [n_rows, k] dtype, row-major, 16B-aligned */
   const void* w;      /* [hidden, k] dtype, row-major (torch Linear.weight layout) */
   int32_t k;
   float alpha;
 } trg_proj_term;
+size_t trg_sage_proj_workspace_bytes(int32_t k_total, int32_t hidden, int dtype);
 int trg_sage_proj_fwd(const trg_proj_term* terms /* host */, int32_t n_terms,
                       const float* bias /* [hidden] fp32, nullable; already alpha-combined */,
                       int64_t n_rows, int32_t hidden, int dtype, int relu,
-                      void* out /* [n_rows, hidden] dtype */, void* stream);
+                      void* out /* [n_rows, hidden] dtype */,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Input-gradient half of the backward of trg_sage_proj_fwd (autograd of F.linear at
+ * train_gnn.py:283, needed for layers >= 2):  d_a_i = row_scale_i * ( alpha_i * dZ @ W_i ),
+ * dZ[n_rows, hidden] = dOut masked by the ReLU.  row_scale (nullable, fp32 [n_rows]) fuses the
+ * 1/deg of the mean aggregation so that K2 is a plain gather-sum.  All k_i must be equal. */
+typedef struct {
+  const void* w;          /* [hidden, k] dtype */
+  int32_t k;
+  float alpha;
+  const float* row_scale; /* nullable */
+  void* d_a;              /* [n_rows, k] dtype, out */
+} trg_proj_bwd_term;
+int trg_sage_proj_bwd_input(const void* dz, const trg_proj_bwd_term* terms /* host */, int32_t n_terms,
+                            int64_t n_rows, int32_t hidden, int dtype,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- A9+A10 / K5: score contraction + top-k ---------------------------------------------------
  * Replaces scores = torch.mm(user_emb, known_post_emb.T); torch.topk(scores, min(K, n))

@@ -203,11 +203,15 @@ def test_link_bce_deterministic(dev):
 
 # ---------------------------------------------------------------------------------------- K3
 @pytest.mark.parametrize("n,h,ks,dtype,tol", [
-    (1000, 64, (64, 64, 64, 64), torch.float32, TOL_F32),
+    (1000, 64, (64, 64, 64, 64), torch.float32, TOL_F32),      # tcgen05 3xTF32, 4 terms, tail tile
     (777, 128, (128, 128), torch.float32, TOL_F32),
+    (128 * 200 + 5, 128, (128, 128, 128), torch.float32, TOL_F32),   # > 148 tiles: persistent loop wraps
+    (4000, 256, (256, 256), torch.float32, TOL_F32),
     (1, 64, (64, 64, 64, 64), torch.float32, TOL_F32),
-    (300, 32, (16, 48), torch.float32, TOL_F32),
-    (513, 128, (128, 128, 128), torch.bfloat16, TOL_BF16),
+    (300, 32, (16, 48), torch.float32, TOL_F32),                # not tensor-core shaped -> FMA kernel
+    (513, 128, (128, 128, 128), torch.bfloat16, TOL_BF16),      # tcgen05 kind::f16
+    (20_000, 256, (256, 256), torch.bfloat16, TOL_BF16),
+    (900, 64, (64, 128), torch.bfloat16, TOL_BF16),
 ])
 def test_proj_fwd(dev, n, h, ks, dtype, tol):
     g = torch.Generator().manual_seed(n + h)
@@ -220,6 +224,28 @@ def test_proj_fwd(dev, n, h, ks, dtype, tol):
         out = Fn.sage_proj_fwd([(A.to(dev), W.to(dev), a) for A, W, a in terms], bias.to(dev), relu)
         e = torch.relu(exp) if relu else exp
         assert_close(out.float().cpu(), e, tol, f"proj relu={relu}")
+
+
+@pytest.mark.parametrize("n,h,ks,dtype,tol", [
+    (1000, 128, (128, 128, 128), torch.float32, TOL_F32),
+    (128 * 160 + 77, 64, (64, 64), torch.float32, TOL_F32),
+    (500, 256, (256,), torch.float32, TOL_F32),
+    (300, 32, (16, 16), torch.float32, TOL_F32),                # FMA kernel path
+    (2000, 128, (128, 128), torch.bfloat16, TOL_BF16),
+])
+def test_proj_bwd_input(dev, n, h, ks, dtype, tol):
+    g = torch.Generator().manual_seed(n * 3 + h)
+    dz = torch.randn(n, h, generator=g).to(dtype)
+    ws = [(torch.randn(h, k, generator=g) / h ** 0.5).to(dtype) for k in ks]
+    alphas = [1.0, 0.75, 1.0][:len(ks)]
+    rs = [torch.rand(n, generator=g) if i % 2 == 0 else None for i in range(len(ks))]
+    outs = Fn.sage_proj_bwd_input(dz.to(dev), [(w.to(dev), a, r.to(dev) if r is not None else None)
+                                               for w, a, r in zip(ws, alphas, rs)])
+    for o, w, a, r in zip(outs, ws, alphas, rs):
+        exp = a * (dz.double() @ w.double())
+        if r is not None:
+            exp = exp * r.double()[:, None]
+        assert_close(o.float().cpu(), exp, tol, "proj bwd input")
 
 
 # ---------------------------------------------------------------------------------------- K5

@@ -22,6 +22,10 @@ class TrgProjTerm(ctypes.Structure):
     _fields_ = [("a", _vp), ("w", _vp), ("k", _i32), ("alpha", ctypes.c_float)]
 
 
+class TrgProjBwdTerm(ctypes.Structure):
+    _fields_ = [("w", _vp), ("k", _i32), ("alpha", ctypes.c_float), ("row_scale", _vp), ("d_a", _vp)]
+
+
 #: every symbol ``include/trg_b200.h`` declares -> (restype, argtypes)
 SIGNATURES = {
     "trg_abi_version": (_int, []),
@@ -35,7 +39,11 @@ SIGNATURES = {
     "trg_edge_bce_workspace_bytes": (_sz, [_i64]),
     "trg_edge_bce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _sz, _vp]),
-    "trg_sage_proj_fwd": (_int, [ctypes.POINTER(TrgProjTerm), _i32, _vp, _i64, _i32, _int, _int, _vp, _vp]),
+    "trg_sage_proj_workspace_bytes": (_sz, [_i32, _i32, _int]),
+    "trg_sage_proj_fwd": (_int, [ctypes.POINTER(TrgProjTerm), _i32, _vp, _i64, _i32, _int, _int, _vp,
+                                 _vp, _sz, _vp]),
+    "trg_sage_proj_bwd_input": (_int, [_vp, ctypes.POINTER(TrgProjBwdTerm), _i32, _i64, _i32, _int,
+                                       _vp, _sz, _vp]),
     "trg_score_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "trg_score_topk": (_int, [_vp, _vp, _i64, _i64, _i32, _int, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "trg_topk_merge": (_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),

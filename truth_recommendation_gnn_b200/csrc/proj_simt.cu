@@ -22,6 +22,7 @@ struct ProjArgs {
   float alpha[4];
   int n_terms;
   const float* bias;
+  const float* row_scale;
   int64_t n_rows;
   int hidden;
   int relu;
@@ -97,9 +98,10 @@ __global__ void __launch_bounds__(kThreads) proj_simt(const ProjArgs p) {
     const int64_t r = m0 + ty * 4 + i;
     if (r >= p.n_rows) continue;
     float o[4];
+    const float rs = p.row_scale ? p.row_scale[r] : 1.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      o[j] = acc[i][j] + b[j];
+      o[j] = acc[i][j] * rs + b[j];
       if (p.relu) o[j] = fmaxf(o[j], 0.f);
     }
     if (sizeof(T) == 4) {
@@ -116,9 +118,11 @@ __global__ void __launch_bounds__(kThreads) proj_simt(const ProjArgs p) {
 
 }  // namespace
 
-int proj_simt_launch(const trg_proj_term* terms, int n_terms, const float* bias, int64_t n_rows,
-                     int hidden, int dtype, int relu, void* out, cudaStream_t st) {
+int proj_simt_launch(const trg_proj_term* terms, int n_terms, const float* bias,
+                     const float* row_scale, int64_t n_rows, int hidden, int dtype, int relu, void* out,
+                     cudaStream_t st) {
   ProjArgs p{};
+  p.row_scale = row_scale;
   for (int i = 0; i < n_terms; ++i) {
     p.a[i] = terms[i].a; p.w[i] = terms[i].w; p.k[i] = terms[i].k; p.alpha[i] = terms[i].alpha;
   }

@@ -56,23 +56,30 @@ def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor):
 
 
 class SageAggFn(torch.autograd.Function):
+    """mean aggregation.  ``grad_prescaled``: the incoming gradient has already been multiplied
+    row-wise by 1/deg (fused into the projection backward's epilogue), so the backward is a plain
+    transposed gather-sum."""
+
     @staticmethod
-    def forward(ctx, x_src, rel: RelationGraph):
-        mean, inv_deg = sage_agg_fwd(rel.fwd, x_src)
+    def forward(ctx, x_src, rel: RelationGraph, grad_prescaled: bool = False):
+        want_inv = rel.inv_deg is None
+        mean, inv_deg = sage_agg_fwd(rel.fwd, x_src, want_inv_deg=want_inv)
+        if want_inv:
+            rel.inv_deg = inv_deg          # static per relation: computed by the first forward
         ctx.rel = rel
-        ctx.save_for_backward(inv_deg)
+        ctx.grad_prescaled = grad_prescaled
         return mean
 
     @staticmethod
     def backward(ctx, g_mean):
         if not ctx.needs_input_grad[0]:
-            return None, None
-        (inv_deg,) = ctx.saved_tensors
-        return sage_agg_bwd(ctx.rel.bwd, inv_deg, g_mean), None
+            return None, None, None
+        rel = ctx.rel
+        return sage_agg_bwd(rel.bwd, None if ctx.grad_prescaled else rel.inv_deg, g_mean), None, None
 
 
-def sage_mean_aggregate(x_src: torch.Tensor, rel: RelationGraph) -> torch.Tensor:
-    return SageAggFn.apply(x_src, rel)
+def sage_mean_aggregate(x_src: torch.Tensor, rel: RelationGraph, grad_prescaled: bool = False) -> torch.Tensor:
+    return SageAggFn.apply(x_src, rel, grad_prescaled)
 
 
 # ------------------------------------------------------------------------------------------
@@ -201,6 +208,10 @@ def link_bce_loss(user_emb, post_emb, train_edge_index, neg_p, interaction_type_
 # ------------------------------------------------------------------------------------------
 # K3: projections + combine + ReLU
 # ------------------------------------------------------------------------------------------
+def _proj_bytes(n, ks, hidden, es):
+    return n * (sum(ks) + hidden) * es
+
+
 def sage_proj_fwd(terms, bias, relu: bool):
     """``out = act(sum_i alpha_i * A_i @ W_i^T + bias)``; terms = [(A, W, alpha), ...]."""
     lib = _lib.load()
@@ -216,10 +227,102 @@ def sage_proj_fwd(terms, bias, relu: bool):
         arr[i].a, arr[i].w, arr[i].k, arr[i].alpha = _lib.ptr(a), _lib.ptr(w), a.size(1), float(alpha)
     out = torch.empty(n, hidden, dtype=a0.dtype, device=a0.device)
     b = bias.float().contiguous() if bias is not None else None
-    _lib.check(lib.trg_sage_proj_fwd(arr, len(terms), _lib.ptr(b), n, hidden, _lib.dtype_code(a0.dtype),
-                                     1 if relu else 0, _lib.ptr(out), _lib.stream()),
-               "trg_sage_proj_fwd")
+    ktot = sum(t[0].size(1) for t in terms)
+    code = _lib.dtype_code(a0.dtype)
+    ws_bytes = int(lib.trg_sage_proj_workspace_bytes(ktot, hidden, code))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a0.device)
+    _lib.call("trg_sage_proj_fwd", _proj_bytes(n, [t[0].size(1) for t in terms], hidden, a0.element_size()),
+              lib.trg_sage_proj_fwd, arr, len(terms), _lib.ptr(b), n, hidden, code, 1 if relu else 0,
+              _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream())
     return out
+
+
+def sage_proj_bwd_input(dz, terms):
+    """``d_a_i = row_scale_i * (alpha_i * dZ @ W_i)``; terms = [(W[h,k], alpha, row_scale|None), ...]."""
+    lib = _lib.load()
+    dz = dz.contiguous()
+    n, hidden = dz.shape
+    arr = (_lib.TrgProjBwdTerm * len(terms))()
+    outs, keep = [], []
+    for i, (w, alpha, rs) in enumerate(terms):
+        w = w.contiguous()
+        if w.dtype != dz.dtype:
+            raise _lib.TrgError("projection operands must share one dtype")
+        d_a = torch.empty(n, w.size(1), dtype=dz.dtype, device=dz.device)
+        rs = rs.float().contiguous() if rs is not None else None
+        keep += [w, rs]
+        outs.append(d_a)
+        arr[i].w, arr[i].k, arr[i].alpha = _lib.ptr(w), w.size(1), float(alpha)
+        arr[i].row_scale, arr[i].d_a = _lib.ptr(rs), _lib.ptr(d_a)
+    ktot = sum(t[0].size(1) for t in terms)
+    code = _lib.dtype_code(dz.dtype)
+    ws_bytes = int(lib.trg_sage_proj_workspace_bytes(ktot, hidden, code))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dz.device)
+    _lib.call("trg_sage_proj_bwd_input", n * (len(terms) * hidden + ktot) * dz.element_size(),
+              lib.trg_sage_proj_bwd_input, _lib.ptr(dz), arr, len(terms), n, hidden, code,
+              _lib.ptr(ws), ws_bytes, _lib.stream())
+    return outs
+
+
+class FusedProjFn(torch.autograd.Function):
+    """``out = act(sum_t alpha_t * A_t @ W_t^T + bias)`` with its backward:
+    dZ = dOut * (out > 0);  dA_t = rs_t * alpha_t * dZ @ W_t;  dW_t = alpha_t * dZ^T @ A_t;
+    db = colsum(dZ).  ``row_scales[t]`` (1/deg or None) is folded into dA_t (see SageAggFn)."""
+
+    @staticmethod
+    def forward(ctx, relu, alphas, row_scales, bias, *aw):
+        n_t = len(aw) // 2
+        a_list, w_list = aw[:n_t], aw[n_t:]
+        out = sage_proj_fwd([(a, w, al) for a, w, al in zip(a_list, w_list, alphas)], bias, relu)
+        ctx.relu, ctx.alphas, ctx.row_scales, ctx.n_t = relu, alphas, row_scales, n_t
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        ctx.save_for_backward(out, *a_list, *w_list)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, *rest = ctx.saved_tensors
+        n_t = ctx.n_t
+        a_list, w_list = rest[:n_t], rest[n_t:]
+        g = g.contiguous()
+        dz = torch.ops.aten.threshold_backward(g, out, 0) if ctx.relu else g
+        need_a = [ctx.needs_input_grad[4 + t] for t in range(n_t)]
+        need_w = [ctx.needs_input_grad[4 + n_t + t] for t in range(n_t)]
+        d_a = [None] * n_t
+        idx = [t for t in range(n_t) if need_a[t]]
+        if idx:
+            outs = sage_proj_bwd_input(dz, [(w_list[t], ctx.alphas[t], ctx.row_scales[t]) for t in idx])
+            for t, o in zip(idx, outs):
+                d_a[t] = o
+        d_w = [None] * n_t
+        widx = [t for t in range(n_t) if need_w[t]]
+        if widx:
+            outs = sage_proj_bwd_weight(dz, [(a_list[t], ctx.alphas[t]) for t in widx])
+            for t, o in zip(widx, outs):
+                d_w[t] = o
+        d_b = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            d_b = dz.sum(0, dtype=torch.float32).to(ctx.bias_dtype)
+        return (None, None, None, d_b, *d_a, *d_w)
+
+
+def sage_proj_bwd_weight(dz, terms):
+    """``dW_t = alpha_t * dZ^T @ A_t``; terms = [(A_t, alpha_t), ...]."""
+    outs = []
+    for a, alpha in terms:
+        dw = dz.t() @ a
+        outs.append(dw if alpha == 1.0 else dw * alpha)
+    return outs
+
+
+def fused_projection(terms, bias, relu=True, row_scales=None):
+    """terms = [(A, W, alpha), ...]; returns act(sum alpha A W^T + bias) with a fused backward."""
+    a_list = [t[0] for t in terms]
+    w_list = [t[1] for t in terms]
+    alphas = tuple(float(t[2]) for t in terms)
+    rs = tuple(row_scales) if row_scales is not None else (None,) * len(terms)
+    return FusedProjFn.apply(relu, alphas, rs, bias, *a_list, *w_list)
 
 
 # ------------------------------------------------------------------------------------------

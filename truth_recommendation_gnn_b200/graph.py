@@ -70,6 +70,7 @@ class RelationGraph:
         self.n_src, self.n_dst = int(n_src), int(n_dst)
         self._fwd = None
         self._bwd = None
+        self.inv_deg = None   # fp32 [n_dst], 1 / max(in-degree, 1); filled by the first aggregation
 
     @property
     def fwd(self) -> CSR:

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch.nn.parameter import Parameter, UninitializedParameter
 
 from . import _lib
-from .functional import sage_mean_aggregate
+from .functional import fused_projection, sage_mean_aggregate
 from .graph import relation_graph
 
 REL_DIRECT = ("post", "rev_engages", "user")
@@ -143,11 +143,35 @@ class WeightedRGCN(torch.nn.Module):
         self.w_social = 0.75
 
     def forward(self, x_dict, edge_index_dict):
+        """Same result as train_gnn.py:166-200, computed as three K1 aggregations and two fused
+        K3 projections (relation combine, biases and ReLU in the GEMM epilogue; the shared
+        ``lin_r`` input of the two user convs is multiplied once by ``1.0*W_r,direct +
+        0.75*W_r,social``)."""
         user_x, post_x = x_dict["user"], x_dict["post"]
-        msg_direct = self.msg_direct((post_x, user_x), edge_index_dict[REL_DIRECT])
-        msg_social = self.msg_social((user_x, user_x), edge_index_dict[REL_SOCIAL])
-        user_out = F.relu(self.w_direct * msg_direct + self.w_social * msg_social)
-        post_out = F.relu(self.post_update((user_x, post_x), edge_index_dict[REL_ENGAGE]))
+        if not user_x.is_cuda:
+            raise _lib.TrgError("WeightedRGCN (B200) needs CUDA tensors; there is no CPU fallback")
+        d, s, p = self.msg_direct, self.msg_social, self.post_update
+        for conv, (xs, xd) in ((d, (post_x, user_x)), (s, (user_x, user_x)), (p, (user_x, post_x))):
+            conv.lin_l.materialize(xs.size(-1))
+            conv.lin_r.materialize(xd.size(-1))
+        n_u, n_p = user_x.size(0), post_x.size(0)
+        rel_d = relation_graph(edge_index_dict[REL_DIRECT], n_p, n_u)
+        rel_s = relation_graph(edge_index_dict[REL_SOCIAL], n_u, n_u)
+        rel_e = relation_graph(edge_index_dict[REL_ENGAGE], n_u, n_p)
+        mean_d = sage_mean_aggregate(post_x, rel_d, True)
+        mean_s = sage_mean_aggregate(user_x, rel_s, True)
+        mean_e = sage_mean_aggregate(user_x, rel_e, True)
+        wd, ws = float(self.w_direct), float(self.w_social)
+        w_root = wd * d.lin_r.weight + ws * s.lin_r.weight
+        b_user = None
+        if d.lin_l.bias is not None:
+            b_user = wd * d.lin_l.bias + ws * s.lin_l.bias
+        user_out = fused_projection(
+            [(mean_d, d.lin_l.weight, wd), (mean_s, s.lin_l.weight, ws), (user_x, w_root, 1.0)],
+            b_user, relu=True, row_scales=(rel_d.inv_deg, rel_s.inv_deg, None))
+        post_out = fused_projection(
+            [(mean_e, p.lin_l.weight, 1.0), (post_x, p.lin_r.weight, 1.0)],
+            p.lin_l.bias, relu=True, row_scales=(rel_e.inv_deg, None))
         return {"user": user_out, "post": post_out}
 
 
