@@ -134,6 +134,22 @@ int trg_sage_proj_bwd_input(const void* dz, const trg_proj_bwd_term* terms /* ho
                             int64_t n_rows, int32_t hidden, int dtype,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight-gradient half: dW_i = alpha_i * dZ^T @ A_i (reduction over the node rows) and
+ * db = column sums of dZ (nullable).  Both operands are consumed MN-major from the row-major
+ * tables by tcgen05 (3xTF32 for fp32); per-CTA partials are reduced in a fixed order
+ * (deterministic).  Workspace: trg_sage_proj_dw_workspace_bytes(). */
+typedef struct {
+  const void* a;   /* [n_rows, k] dtype */
+  int32_t k;
+  float alpha;
+  void* d_w;       /* [hidden, k] dtype, out */
+} trg_proj_dw_term;
+size_t trg_sage_proj_dw_workspace_bytes(void);
+int trg_sage_proj_bwd_weight(const void* dz, const trg_proj_dw_term* terms /* host */, int32_t n_terms,
+                             float* d_bias /* [hidden] fp32, nullable */,
+                             int64_t n_rows, int32_t hidden, int dtype,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- A9+A10 / K5: score contraction + top-k ---------------------------------------------------
  * Replaces scores = torch.mm(user_emb, known_post_emb.T); torch.topk(scores, min(K, n))
  * (inference.py:427-428; train_gnn.py:335-341).  Never materialises the score matrix.  Total

@@ -248,6 +248,33 @@ def test_proj_bwd_input(dev, n, h, ks, dtype, tol):
         assert_close(o.float().cpu(), exp, tol, "proj bwd input")
 
 
+@pytest.mark.parametrize("n,h,ks,dtype,tol", [
+    (1000, 128, (128, 128, 128), torch.float32, TOL_F32),      # tcgen05 MN-major 3xTF32
+    (50_000, 128, (128, 128), torch.float32, TOL_F32),
+    (7, 128, (128,), torch.float32, TOL_F32),                   # fewer rows than one k-block
+    (3000, 64, (64, 64, 64), torch.float32, TOL_F32),           # hidden < 128: TMA zero fill
+    (3000, 256, (256, 256), torch.float32, TOL_F32),            # two 128-wide blocks of hidden
+    (2000, 128, (64, 256), torch.float32, TOL_F32),             # mixed widths
+    (300, 32, (16, 48), torch.float32, TOL_F32),                # generic FMA path
+    (5000, 128, (128, 128, 128), torch.bfloat16, TOL_BF16),
+    (5000, 256, (256, 256), torch.bfloat16, TOL_BF16),
+])
+def test_proj_bwd_weight(dev, n, h, ks, dtype, tol):
+    g = torch.Generator().manual_seed(n * 7 + h)
+    dz = torch.randn(n, h, generator=g).to(dtype)
+    dz[torch.rand(n, h, generator=g) < 0.5] = 0            # post-ReLU-mask sparsity
+    A = [torch.randn(n, k, generator=g).to(dtype) for k in ks]
+    alphas = [1.0, 0.75, 1.0][:len(ks)]
+    outs, db = Fn.sage_proj_bwd_weight(dz.to(dev), [(a.to(dev), al) for a, al in zip(A, alphas)], True)
+    for o, a, al in zip(outs, A, alphas):
+        exp = al * (dz.double().t() @ a.double())
+        assert o.shape == exp.shape
+        assert_close(o.float().cpu(), exp, tol, "dW")
+    assert_close(db.cpu(), dz.double().sum(0), tol, "db")
+    outs2, db2 = Fn.sage_proj_bwd_weight(dz.to(dev), [(a.to(dev), al) for a, al in zip(A, alphas)], True)
+    assert all(torch.equal(x, y) for x, y in zip(outs, outs2)) and torch.equal(db, db2)   # deterministic
+
+
 # ---------------------------------------------------------------------------------------- K5
 @pytest.mark.parametrize("b,p,h,k", [(1, 20_000, 64, 10), (37, 5000, 64, 10), (64, 3000, 128, 100),
                                      (5, 7, 64, 10), (3, 1000, 16, 3), (130, 2500, 256, 128)])

@@ -26,6 +26,10 @@ class TrgProjBwdTerm(ctypes.Structure):
     _fields_ = [("w", _vp), ("k", _i32), ("alpha", ctypes.c_float), ("row_scale", _vp), ("d_a", _vp)]
 
 
+class TrgProjDwTerm(ctypes.Structure):
+    _fields_ = [("a", _vp), ("k", _i32), ("alpha", ctypes.c_float), ("d_w", _vp)]
+
+
 #: every symbol ``include/trg_b200.h`` declares -> (restype, argtypes)
 SIGNATURES = {
     "trg_abi_version": (_int, []),
@@ -44,6 +48,9 @@ SIGNATURES = {
                                  _vp, _sz, _vp]),
     "trg_sage_proj_bwd_input": (_int, [_vp, ctypes.POINTER(TrgProjBwdTerm), _i32, _i64, _i32, _int,
                                        _vp, _sz, _vp]),
+    "trg_sage_proj_dw_workspace_bytes": (_sz, []),
+    "trg_sage_proj_bwd_weight": (_int, [_vp, ctypes.POINTER(TrgProjDwTerm), _i32, _vp, _i64, _i32, _int,
+                                        _vp, _sz, _vp]),
     "trg_score_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "trg_score_topk": (_int, [_vp, _vp, _i64, _i64, _i32, _int, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "trg_topk_merge": (_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),

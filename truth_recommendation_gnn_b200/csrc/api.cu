@@ -29,6 +29,12 @@ int proj_tc_bwd_input(const void* dz, const trg_proj_bwd_term* terms, int n_term
                       int hidden, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 int proj_simt_bwd_input(const void* dz, const trg_proj_bwd_term* terms, int n_terms, int64_t n_rows,
                         int hidden, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t proj_dw_workspace_bytes();
+bool proj_dw_eligible(const int* ks, int n_terms, int hidden, int dtype);
+int proj_tc_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_terms, float* db,
+                       int64_t n_rows, int hidden, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+int proj_simt_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_terms, float* db,
+                         int64_t n_rows, int hidden, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace tc
 
 static bool force_simt() {
@@ -100,4 +106,31 @@ extern "C" int trg_sage_proj_bwd_input(const void* dz, const trg_proj_bwd_term* 
   if (!force_simt() && same_k && tc::proj_tc_eligible(kh, 1, terms[0].k, dtype))
     return tc::proj_tc_bwd_input(dz, terms, n_terms, n_rows, hidden, dtype, workspace, workspace_bytes, st);
   return tc::proj_simt_bwd_input(dz, terms, n_terms, n_rows, hidden, dtype, workspace, workspace_bytes, st);
+}
+
+extern "C" size_t trg_sage_proj_dw_workspace_bytes(void) { return tc::proj_dw_workspace_bytes(); }
+
+extern "C" int trg_sage_proj_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int32_t n_terms,
+                                        float* d_bias, int64_t n_rows, int32_t hidden, int dtype,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  TRG_CHECK_ARG(n_terms >= 0 && n_terms <= 4 && (n_terms == 0 || terms), "trg_sage_proj_bwd_weight: n_terms=%d not in 0..4", n_terms);
+  TRG_CHECK_ARG(dtype == TRG_F32 || dtype == TRG_BF16, "trg_sage_proj_bwd_weight: unknown dtype %d", dtype);
+  TRG_CHECK_ARG(n_rows >= 0 && hidden > 0 && hidden <= 512, "trg_sage_proj_bwd_weight: bad n_rows/hidden");
+  const int es = dtype == TRG_BF16 ? 2 : 4;
+  TRG_CHECK_ARG(n_rows == 0 || (dz && (uintptr_t)dz % 16 == 0 && (hidden * es) % 16 == 0),
+                "trg_sage_proj_bwd_weight: dz must be 16-byte aligned with 16-byte-multiple rows");
+  int ks[4];
+  for (int i = 0; i < n_terms; ++i) {
+    TRG_CHECK_ARG(terms[i].d_w && terms[i].k > 0 && terms[i].k <= 512 && (n_rows == 0 || terms[i].a),
+                  "trg_sage_proj_bwd_weight: bad term %d", i);
+    TRG_CHECK_ARG((uintptr_t)terms[i].a % 16 == 0 && (terms[i].k * es) % 16 == 0,
+                  "trg_sage_proj_bwd_weight: term %d needs 16-byte aligned rows", i);
+    ks[i] = terms[i].k;
+  }
+  if (!force_simt() && tc::proj_dw_eligible(ks, n_terms, hidden, dtype))
+    return tc::proj_tc_bwd_weight(dz, terms, n_terms, d_bias, n_rows, hidden, dtype, workspace,
+                                  workspace_bytes, st);
+  return tc::proj_simt_bwd_weight(dz, terms, n_terms, d_bias, n_rows, hidden, dtype, workspace,
+                                  workspace_bytes, st);
 }

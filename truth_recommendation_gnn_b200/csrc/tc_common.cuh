@@ -159,7 +159,7 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
                  uint64_t ld_elems, uint32_t box_rows);
 // 3-D view (32-element column chunk, rows, column chunk index) for MN-major operands.
 int make_tmap_mn(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
-                 uint64_t ld_elems, uint32_t box_rows);
+                 uint64_t ld_elems, uint32_t box_rows, uint32_t box_chunks);
 
 }  // namespace tc
 }  // namespace trg

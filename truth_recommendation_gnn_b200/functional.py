@@ -297,23 +297,39 @@ class FusedProjFn(torch.autograd.Function):
                 d_a[t] = o
         d_w = [None] * n_t
         widx = [t for t in range(n_t) if need_w[t]]
-        if widx:
-            outs = sage_proj_bwd_weight(dz, [(a_list[t], ctx.alphas[t]) for t in widx])
+        want_b = ctx.has_bias and ctx.needs_input_grad[3]
+        d_b = None
+        if widx or want_b:
+            outs, d_b = sage_proj_bwd_weight(dz, [(a_list[t], ctx.alphas[t]) for t in widx], want_b)
             for t, o in zip(widx, outs):
                 d_w[t] = o
-        d_b = None
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            d_b = dz.sum(0, dtype=torch.float32).to(ctx.bias_dtype)
+            if d_b is not None:
+                d_b = d_b.to(ctx.bias_dtype)
         return (None, None, None, d_b, *d_a, *d_w)
 
 
-def sage_proj_bwd_weight(dz, terms):
-    """``dW_t = alpha_t * dZ^T @ A_t``; terms = [(A_t, alpha_t), ...]."""
-    outs = []
-    for a, alpha in terms:
-        dw = dz.t() @ a
-        outs.append(dw if alpha == 1.0 else dw * alpha)
-    return outs
+def sage_proj_bwd_weight(dz, terms, want_bias: bool):
+    """``dW_t = alpha_t * dZ^T @ A_t`` and ``db = colsum(dZ)``; terms = [(A_t, alpha_t), ...].
+    Returns ``([dW_t...], db fp32 | None)``."""
+    lib = _lib.load()
+    dz = dz.contiguous()
+    n, hidden = dz.shape
+    arr = (_lib.TrgProjDwTerm * max(len(terms), 1))()
+    outs, keep = [], []
+    for i, (a, alpha) in enumerate(terms):
+        a = a.contiguous()
+        d_w = torch.empty(hidden, a.size(1), dtype=dz.dtype, device=dz.device)
+        keep.append(a)
+        outs.append(d_w)
+        arr[i].a, arr[i].k, arr[i].alpha, arr[i].d_w = _lib.ptr(a), a.size(1), float(alpha), _lib.ptr(d_w)
+    db = torch.empty(hidden, dtype=torch.float32, device=dz.device) if want_bias else None
+    ws_bytes = int(lib.trg_sage_proj_dw_workspace_bytes())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dz.device)
+    ktot = sum(t[0].size(1) for t in terms)
+    _lib.call("trg_sage_proj_bwd_weight", n * (hidden + ktot) * dz.element_size(),
+              lib.trg_sage_proj_bwd_weight, _lib.ptr(dz), arr, len(terms), _lib.ptr(db), n, hidden,
+              _lib.dtype_code(dz.dtype), _lib.ptr(ws), ws_bytes, _lib.stream())
+    return outs, db
 
 
 def fused_projection(terms, bias, relu=True, row_scales=None):
