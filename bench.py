@@ -160,7 +160,7 @@ def run_reference_arm(args, w):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, **{k: w[k] for k in ("num_users", "num_posts", "e_eng", "e_soc", "hidden", "layers")},
                    "note": "CPU arm runs a bounded sample of this workload, see cpu_baseline.sample"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -176,28 +176,38 @@ def run_reference_arm(args, w):
 def gpu_train_bench(args, w, rank, world, dev):
     import truth_recommendation_gnn_b200 as trg
     from truth_recommendation_gnn_b200 import _lib, synth
+    from truth_recommendation_gnn_b200 import dist as tdist
 
     dtype = torch.float32 if w["dtype"] == "f32" else torch.bfloat16
     U, P, Ee, Es, H, L = w["num_users"], w["num_posts"], w["e_eng"], w["e_soc"], w["hidden"], w["layers"]
     t_setup0 = time.perf_counter()
-    g = synth.synth_graph(U, P, Ee, Es, H, seed=0, device=dev, dtype=dtype)
+    g = synth.synth_graph(U, P, Ee, Es, H, seed=0, device=dev, dtype=dtype)   # same graph on every rank
     model = trg.WeightedRGCN(H) if L == 1 else trg.StackedWeightedRGCN(H, L)
     model.load_state_dict(synth.init_state_dict(H, H, L))
     model = model.to(dev).to(dtype)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    # this step's host input: the sampled negatives (train_gnn.py:272), pinned
     n_host = 4
-    neg_host = [synth.synth_neg(P, Ee, i).pin_memory() for i in range(n_host)]
-    neg_dev = [t.to(dev) for t in neg_host]
+    shard = None
+    if world > 1:
+        # destination partition: this rank keeps its rows / edges and drops the full graph
+        shard = tdist.ShardedGraph(g.x_dict, g.edge_index_dict, g.train_edge_index,
+                                   g.interaction_type_tensor, U, P)
+        negs = [synth.synth_neg(P, Ee, i, device=dev)[shard.pos_mask].contiguous() for i in range(n_host)]
+        del g
+        torch.cuda.empty_cache()
+    else:
+        negs = [synth.synth_neg(P, Ee, i, device=dev) for i in range(n_host)]
+    # this step's host input: the sampled negatives (train_gnn.py:272), pinned
+    neg_host = [t.cpu().pin_memory() for t in negs]
+    neg_dev = negs
     torch.cuda.synchronize()
 
     def step(i, e2e):
-        if e2e:
-            neg = neg_host[i % n_host].to(dev, non_blocking=True)
-            return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
-                                  g.interaction_type_tensor, U, P, neg_p=neg)          # loss.item(): D2H
+        neg = neg_host[i % n_host].to(dev, non_blocking=True) if e2e else neg_dev[i % n_host]
+        if world > 1:
+            return tdist.train_step_sharded(model, opt, shard, neg_p_local=neg, return_tensor=not e2e)
         return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
-                              g.interaction_type_tensor, U, P, neg_p=neg_dev[i % n_host], return_tensor=True)
+                              g.interaction_type_tensor, U, P, neg_p=neg, return_tensor=not e2e)
 
     for i in range(args.warmup):
         step(i, False)
@@ -239,13 +249,18 @@ def gpu_train_bench(args, w, rank, world, dev):
     torch.cuda.synchronize(); barrier()
     ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
 
+    launches = n1 - n0
+    h2d = int(neg_host[0].numel()) * 8
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+        c = torch.tensor([launches, h2d], device=dev, dtype=torch.int64)
+        torch.distributed.all_reduce(c)
+        launches, h2d = int(c[0]), int(c[1])
     mp_edges = L * (2 * Ee + Es)
-    return dict(ms=ms, ms_e2e=ms_e2e, mp_edges=mp_edges, prof=prof, launches=(n1 - n0), clocks=clk,
-                setup_s=setup_s, h2d=Ee * 8, d2h=4, mem_gb=torch.cuda.max_memory_allocated(dev) / 2**30)
+    return dict(ms=ms, ms_e2e=ms_e2e, mp_edges=mp_edges, prof=prof, launches=launches, clocks=clk,
+                setup_s=setup_s, h2d=h2d, d2h=4 * world, mem_gb=torch.cuda.max_memory_allocated(dev) / 2**30)
 
 
 def gpu_topk_bench(args, dev, n_post, hidden, k=100, batch=4096, iters=3):
@@ -281,7 +296,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
-        args.workload = "cfg2" if world == 1 else "cfg3"
+        args.workload = "cfg2"   # the same graph at every N: the driver's scaling ratio compares like with like
     w = WORKLOADS[args.workload]
 
     if args.impl == "reference":
@@ -296,11 +311,7 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
 
-    if world > 1:
-        from truth_recommendation_gnn_b200 import dist as tdist
-        r = tdist.bench_train(args, w, rank, world, dev)
-    else:
-        r = gpu_train_bench(args, w, rank, world, dev)
+    r = gpu_train_bench(args, w, rank, world, dev)
 
     if rank == 0:
         pk = peaks()
@@ -317,7 +328,7 @@ def main():
         sb = step_bytes(w, elem)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['num_users']} users / {w['num_posts']} posts / "
                                    f"{w['e_eng'] + w['e_soc']} edges, {w['layers']}-layer hetero SAGE hidden={w['hidden']} "

@@ -86,7 +86,9 @@ int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* ei
  *     loss = wbar * mean(softplus(-pos)) + mean(softplus(neg)),   wbar = mean(w[pos_p + U])
  * (the reference's BCEWithLogitsLoss is a scalar mean, so its "weighted" loss is exactly this).
  * Positive edges are given grouped by user: rowptr_u/col_p/eid = trg_csr_build(other = pos_p,
- * key = pos_u).  neg_p is in ORIGINAL edge order (index it with eid).
+ * key = pos_u).  neg_p is in ORIGINAL edge order (index it with eid).  The edges processed are
+ * those of rowptr_u; n_edges is the E of the two means (the GLOBAL number of positives when the
+ * caller holds one partition of them, so that partial losses and gradients add up).
  * Outputs: loss_out[1]; and when c_pos/c_neg/g_u are non-NULL the backward ingredients
  *     c_pos[e] = dloss/dpos_e,  c_neg[e] = dloss/dneg_e   (original edge order)
  *     g_u[r]   = sum_e c_pos[e] p[pos_p[e]] + c_neg[e] p[neg_p[e]]   (dloss/du, dtype rows)

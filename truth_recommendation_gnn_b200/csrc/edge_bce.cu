@@ -251,8 +251,7 @@ extern "C" int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, c
   TRG_CHECK_ARG(loss_out && wbar, "trg_edge_bce_fwd: NULL loss_out/wbar");
   TRG_CHECK_ARG((c_pos == nullptr) == (g_u == nullptr) && (c_neg == nullptr) == (g_u == nullptr),
                 "trg_edge_bce_fwd: c_pos, c_neg and g_u must be all NULL or all non-NULL");
-  TRG_CHECK_ARG(n_edges == 0 || (rowptr_u && col_p && eid && neg_p && u && p),
-                "trg_edge_bce_fwd: NULL input with n_edges > 0");
+  TRG_CHECK_ARG(n_users == 0 || (rowptr_u && u && p), "trg_edge_bce_fwd: NULL rowptr / tables");
   TRG_CHECK_ARG(((uintptr_t)u | (uintptr_t)p | (uintptr_t)g_u) % 16 == 0,
                 "trg_edge_bce_fwd: tables must be 16-byte aligned");
   const int es = dtype == TRG_BF16 ? 2 : 4;

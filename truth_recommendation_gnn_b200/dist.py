@@ -1,0 +1,218 @@
+"""Multi-GPU execution of the hot path: destination-node partitioning.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the B200 box, gloo in the CPU
+tests of this host logic).  Rank g owns a contiguous range of users and of posts, the CSR rows of
+all three relations whose destination falls in its ranges, and the matching activation rows.
+Per layer the user table and the post table are all-gathered ONCE each (users feed two relations);
+the backward of that gather is a reduce-scatter of the source-gradient partials; weight gradients
+are all-reduced as one flat buffer.  The loss partitions the positive edges by owner of ``pos_u``.
+Inference shards the catalogue by post-id range and merges per-shard top-k lists.
+
+The reference has no distributed code at all (single process, single device: train_gnn.py:205);
+this is the scaling axis BASELINE.json asks for.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .graph import RelationGraph
+from .nn import CUDA_OPS, REL_DIRECT, REL_ENGAGE, REL_SOCIAL, StackedWeightedRGCN, WeightedRGCN
+
+
+def chunk_of(n: int, world: int) -> int:
+    return (n + world - 1) // world
+
+
+# ------------------------------------------------------------------------------------------
+# collectives with autograd
+# ------------------------------------------------------------------------------------------
+def _all_gather_rows(x_local: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    out = torch.empty(world * x_local.size(0), *x_local.shape[1:], dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(out, x_local.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_rows(g_full: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    chunk = g_full.size(0) // world
+    g_full = g_full.contiguous()
+    if dist.get_backend(group) == "gloo":      # gloo has no reduce_scatter: all_reduce + slice
+        dist.all_reduce(g_full, group=group)
+        return g_full[rank * chunk:(rank + 1) * chunk].clone()
+    out = torch.empty(chunk, *g_full.shape[1:], dtype=g_full.dtype, device=g_full.device)
+    dist.reduce_scatter_tensor(out, g_full, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+class AllGatherRows(torch.autograd.Function):
+    """[chunk, F] per rank -> [world*chunk, F]; backward = reduce-scatter (sum) of the partials."""
+
+    @staticmethod
+    def forward(ctx, x_local):
+        return _all_gather_rows(x_local)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        return _reduce_scatter_rows(g_full)
+
+
+def all_gather_rows(x_local):
+    if x_local.requires_grad:
+        return AllGatherRows.apply(x_local)
+    return _all_gather_rows(x_local)
+
+
+# ------------------------------------------------------------------------------------------
+# partitioned graph
+# ------------------------------------------------------------------------------------------
+class ShardedGraph:
+    """This rank's share of the graph, built from the full COO ``edge_index_dict`` (reference
+    format).  Source ids stay global (row r of an all-gathered table is global id r because the
+    ranges are contiguous chunks); destination ids become local."""
+
+    def __init__(self, x_dict, edge_index_dict, train_edge_index, interaction_type_tensor,
+                 num_users, num_posts, rank=None, world=None):
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.num_users, self.num_posts = int(num_users), int(num_posts)
+        self.cu, self.cp = chunk_of(num_users, self.world), chunk_of(num_posts, self.world)
+        self.u0, self.p0 = self.rank * self.cu, self.rank * self.cp
+        self.u1, self.p1 = min(self.u0 + self.cu, num_users), min(self.p0 + self.cp, num_posts)
+        n_of = {"user": (self.u0, self.u1, self.cu), "post": (self.p0, self.p1, self.cp)}
+        # owned feature rows, zero-padded to the chunk size so every rank gathers equal shapes
+        self.x_local = {}
+        for t, (a, b, c) in n_of.items():
+            x = x_dict[t]
+            xl = torch.zeros(c, x.size(1), dtype=x.dtype, device=x.device)
+            xl[:max(b - a, 0)] = x[a:b]
+            self.x_local[t] = xl
+        # per relation: edges whose destination is owned; dst -> local id
+        self.rels = {}
+        self.n_local_edges = {}
+        for rel in (REL_DIRECT, REL_SOCIAL, REL_ENGAGE):
+            ei = edge_index_dict[rel]
+            a, b, c = n_of[rel[2]]
+            m = (ei[1] >= a) & (ei[1] < b)
+            loc = torch.stack([ei[0][m], ei[1][m] - a]).contiguous()
+            n_src_pad = n_of[rel[0]][2] * self.world
+            self.rels[rel] = RelationGraph(loc, n_src_pad, c)
+            self.n_local_edges[rel] = int(loc.size(1))
+        # loss: positives owned by the owner of pos_u (train_gnn.py:259-281)
+        pos_u, pos_p = train_edge_index[0], train_edge_index[1]
+        self.pos_mask = (pos_u >= self.u0) & (pos_u < self.u1)
+        self.train_local = torch.stack([pos_u[self.pos_mask] - self.u0, pos_p[self.pos_mask]]).contiguous()
+        self.n_pos_global = int(train_edge_index.size(1))
+        w = interaction_type_tensor[pos_p[self.pos_mask] + num_users].float()
+        wsum = torch.stack([w.sum(), torch.tensor(float(w.numel()), device=w.device)])
+        if self.world > 1:
+            dist.all_reduce(wsum)
+        self.wbar = (wsum[0] / wsum[1]).reshape(1).float().contiguous()
+        self._layer0_src = None
+
+    def layer0_sources(self):
+        """Input features are static: gather them once (train_gnn.py:211 moves the graph once)."""
+        if self._layer0_src is None:
+            self._layer0_src = {t: _all_gather_rows(x) for t, x in self.x_local.items()}
+        return self._layer0_src
+
+
+def forward_sharded(model, shard: ShardedGraph, ops=CUDA_OPS):
+    """Forward of ``WeightedRGCN`` / ``StackedWeightedRGCN`` on this rank's destination rows."""
+    layers = list(model.layers) if isinstance(model, StackedWeightedRGCN) else [model]
+    dst = shard.x_local
+    for i, layer in enumerate(layers):
+        src = shard.layer0_sources() if i == 0 else {t: all_gather_rows(x) for t, x in dst.items()}
+        dst = layer.forward_partitioned(src, dst, shard.rels, ops)
+    return dst
+
+
+class CudaLossOps:
+    @staticmethod
+    def link_loss(user_local, post_full, shard: ShardedGraph, neg_local):
+        from .functional import LinkBCEFn, LinkStructure
+        ls = getattr(shard, "_link", None)
+        if ls is None:
+            ls = LinkStructure.__new__(LinkStructure)
+            from .graph import build_csr
+            pu, pp = shard.train_local[0], shard.train_local[1]
+            n_post_pad = shard.cp * shard.world
+            ls.train_edge_index = shard.train_local
+            ls.num_users, ls.num_posts = shard.cu, n_post_pad
+            ls.n_edges = int(pu.numel())
+            ls.by_user = build_csr(pp, pu, shard.cu, n_post_pad)
+            ls.by_post = build_csr(pu, pp, n_post_pad, shard.cu, validate=False)
+            ls.wbar = shard.wbar
+            ls.n_edges_scale = shard.n_pos_global
+            shard._link = ls
+        return LinkBCEFn.apply(user_local, post_full, neg_local, ls)
+
+
+CUDA_LOSS_OPS = CudaLossOps()
+
+
+def allreduce_grads(params):
+    """One flat all-reduce (sum) of every weight gradient (9*L small tensors: latency-bound)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or dist.get_world_size() == 1:
+        return
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    dist.all_reduce(flat)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def train_step_sharded(model, optimizer, shard: ShardedGraph, neg_p_global=None, neg_p_local=None,
+                       ops=CUDA_OPS, loss_ops=CUDA_LOSS_OPS, return_tensor=False):
+    """The body of ``train()`` (train_gnn.py:242-285) on a destination partition.  Every rank holds
+    the same weights; the returned loss is the global loss (identical on all ranks)."""
+    model.train()
+    optimizer.zero_grad()
+    out = forward_sharded(model, shard, ops)
+    post_full = all_gather_rows(out["post"])
+    if neg_p_local is None:
+        if neg_p_global is None:
+            neg_p_local = torch.randint(0, shard.num_posts, (shard.train_local.size(1),),
+                                        device=out["user"].device)
+        else:
+            neg_p_local = neg_p_global[shard.pos_mask].contiguous()
+    loss_local = loss_ops.link_loss(out["user"], post_full, shard, neg_p_local)
+    loss_local.backward()
+    allreduce_grads(list(model.parameters()))
+    optimizer.step()
+    loss = loss_local.detach().clone()
+    if shard.world > 1:
+        dist.all_reduce(loss)
+    return loss if return_tensor else loss.item()
+
+
+@torch.no_grad()
+def recommend_sharded(q, cat_local, k, id_offset, score_topk_fn=None, merge_fn=None):
+    """Catalogue sharded by post-id range: local score + top-k, all-gather of the per-shard
+    ``(values, global ids)``, merge under (score desc, id asc) == the unsharded result."""
+    from . import functional as Fn
+    score_topk_fn = score_topk_fn or Fn.score_topk
+    merge_fn = merge_fn or Fn.topk_merge
+    world = dist.get_world_size()
+    vals, ids = score_topk_fn(q, cat_local, k, id_offset)
+    kk = vals.size(1)
+    if world == 1:
+        return vals, ids
+    # shards may hold fewer than k posts: pad lists so every rank contributes k columns
+    if kk < k:
+        pad = k - kk
+        vals = torch.cat([vals, torch.full((vals.size(0), pad), float("-inf"), device=vals.device)], 1)
+        ids = torch.cat([ids, torch.full((ids.size(0), pad), torch.iinfo(torch.int64).max, device=ids.device)], 1)
+    b = vals.size(0)
+    av = torch.empty(world * b, k, dtype=vals.dtype, device=vals.device)
+    ai = torch.empty(world * b, k, dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(av, vals.contiguous())
+    dist.all_gather_into_tensor(ai, ids.contiguous())
+    av = av.view(world, b, k).permute(1, 0, 2).reshape(b, -1).contiguous()
+    ai = ai.view(world, b, k).permute(1, 0, 2).reshape(b, -1).contiguous()
+    return merge_fn(av, ai, world, k)

@@ -159,12 +159,14 @@ def edge_bce_fwd(ls: LinkStructure, user_emb, post_emb, neg_p, want_grad: bool):
     ws_bytes = int(lib.trg_edge_bce_workspace_bytes(ls.num_users))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     e = ls.n_edges
+    # 1/E scale of the means: the GLOBAL positive count when this rank holds a partition of them
+    e_scale = int(getattr(ls, "n_edges_scale", e))
     rb = user_emb.size(1) * user_emb.element_size()
     nbytes = e * (2 * rb + 16 + (8 if want_grad else 0)) + ls.num_users * (rb * (2 if want_grad else 1) + 4)
     _lib.call("trg_edge_bce_fwd", nbytes, lib.trg_edge_bce_fwd,
               _lib.ptr(ls.by_user.rowptr), _lib.ptr(ls.by_user.col) if e else None,
               _lib.ptr(ls.by_user.eid) if e else None, _lib.ptr(neg_p) if e else None,
-              _lib.ptr(user_emb), _lib.ptr(post_emb), ls.num_users, e, user_emb.size(1),
+              _lib.ptr(user_emb), _lib.ptr(post_emb), ls.num_users, e_scale, user_emb.size(1),
               _lib.dtype_code(user_emb.dtype), _lib.ptr(ls.wbar), _lib.ptr(loss), _lib.ptr(c_pos),
               _lib.ptr(c_neg), _lib.ptr(g_u), _lib.ptr(ws), ws_bytes, _lib.stream())
     return loss, c_pos, c_neg, g_u

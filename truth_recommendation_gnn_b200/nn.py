@@ -150,29 +150,57 @@ class WeightedRGCN(torch.nn.Module):
         user_x, post_x = x_dict["user"], x_dict["post"]
         if not user_x.is_cuda:
             raise _lib.TrgError("WeightedRGCN (B200) needs CUDA tensors; there is no CPU fallback")
+        n_u, n_p = user_x.size(0), post_x.size(0)
+        rels = {REL_DIRECT: relation_graph(edge_index_dict[REL_DIRECT], n_p, n_u),
+                REL_SOCIAL: relation_graph(edge_index_dict[REL_SOCIAL], n_u, n_u),
+                REL_ENGAGE: relation_graph(edge_index_dict[REL_ENGAGE], n_u, n_p)}
+        return self.forward_partitioned(x_dict, x_dict, rels, CUDA_OPS)
+
+    def forward_partitioned(self, src_dict, dst_dict, rels, ops):
+        """One hetero layer on a destination partition: ``src_dict`` holds the source tables (all
+        rows: the all-gathered tables on multi-GPU), ``dst_dict`` the owned destination rows,
+        ``rels`` one :class:`RelationGraph` per relation (rows = owned destinations).  Single GPU:
+        ``src_dict is dst_dict``."""
+        user_src, post_src = src_dict["user"], src_dict["post"]
+        user_x, post_x = dst_dict["user"], dst_dict["post"]
         d, s, p = self.msg_direct, self.msg_social, self.post_update
-        for conv, (xs, xd) in ((d, (post_x, user_x)), (s, (user_x, user_x)), (p, (user_x, post_x))):
+        for conv, (xs, xd) in ((d, (post_src, user_x)), (s, (user_src, user_x)), (p, (user_src, post_x))):
             conv.lin_l.materialize(xs.size(-1))
             conv.lin_r.materialize(xd.size(-1))
-        n_u, n_p = user_x.size(0), post_x.size(0)
-        rel_d = relation_graph(edge_index_dict[REL_DIRECT], n_p, n_u)
-        rel_s = relation_graph(edge_index_dict[REL_SOCIAL], n_u, n_u)
-        rel_e = relation_graph(edge_index_dict[REL_ENGAGE], n_u, n_p)
-        mean_d = sage_mean_aggregate(post_x, rel_d, True)
-        mean_s = sage_mean_aggregate(user_x, rel_s, True)
-        mean_e = sage_mean_aggregate(user_x, rel_e, True)
+        rel_d, rel_s, rel_e = rels[REL_DIRECT], rels[REL_SOCIAL], rels[REL_ENGAGE]
+        mean_d = ops.aggregate(post_src, rel_d)
+        mean_s = ops.aggregate(user_src, rel_s)
+        mean_e = ops.aggregate(user_src, rel_e)
         wd, ws = float(self.w_direct), float(self.w_social)
         w_root = wd * d.lin_r.weight + ws * s.lin_r.weight
         b_user = None
         if d.lin_l.bias is not None:
             b_user = wd * d.lin_l.bias + ws * s.lin_l.bias
-        user_out = fused_projection(
+        user_out = ops.project(
             [(mean_d, d.lin_l.weight, wd), (mean_s, s.lin_l.weight, ws), (user_x, w_root, 1.0)],
-            b_user, relu=True, row_scales=(rel_d.inv_deg, rel_s.inv_deg, None))
-        post_out = fused_projection(
+            b_user, True, (rel_d, rel_s, None))
+        post_out = ops.project(
             [(mean_e, p.lin_l.weight, 1.0), (post_x, p.lin_r.weight, 1.0)],
-            p.lin_l.bias, relu=True, row_scales=(rel_e.inv_deg, None))
+            p.lin_l.bias, True, (rel_e, None))
         return {"user": user_out, "post": post_out}
+
+
+class CudaOps:
+    """The sm_100a kernels behind the model (K1/K2 aggregation, K3 projections).  ``aggregate``
+    returns a mean whose gradient is expected pre-scaled by 1/deg; ``project`` folds that scale
+    into its input-gradient epilogue (``scale_rels`` names the relation of each mean term)."""
+
+    @staticmethod
+    def aggregate(x_src, rel):
+        return sage_mean_aggregate(x_src, rel, True)
+
+    @staticmethod
+    def project(terms, bias, relu, scale_rels):
+        rs = tuple(r.inv_deg if r is not None else None for r in scale_rels)
+        return fused_projection(terms, bias, relu=relu, row_scales=rs)
+
+
+CUDA_OPS = CudaOps()
 
 
 class StackedWeightedRGCN(torch.nn.Module):
