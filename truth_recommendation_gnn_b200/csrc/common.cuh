@@ -77,6 +77,10 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+// Bulk L2 prefetch of a whole table row (bytes: multiple of 16, address 16-byte aligned).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // Output rows written once: streaming store.
 __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),

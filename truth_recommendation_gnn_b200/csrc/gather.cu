@@ -141,6 +141,144 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
   }
 }
 
+// v2: each group of LPR lanes owns R CONSECUTIVE destination rows and walks their edges as one
+// continuous stream (the CSR stores them back to back): neighbour ids for the next 32-edge chunk
+// are prefetched while the current chunk's rows are in flight, and the running sum is flushed at
+// row boundaries.  Removes the per-row rowptr -> col -> row dependency chain that made short rows
+// (in-degree ~8) latency-bound (profiles/README.md, r1_v1).  Same CSR-order adds: still bit-exact.
+template <typename T, int LPR, int VPL, int MODE, int R>
+__global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(const GatherArgs a) {
+  constexpr int kVec = Elem<T>::kVec;
+  constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
+  static_assert(R < LPR, "row boundaries are held one per lane");
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPR - 1);
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+  const int64_t r0 = ((int64_t)blockIdx.x * (kThreads / LPR) + threadIdx.x / LPR) * R;
+  if (r0 >= a.n_rows) return;
+  const int nr = (int)((a.n_rows - r0) < (int64_t)R ? (a.n_rows - r0) : (int64_t)R);
+  const int my_ptr = ldg_stream(a.rowptr + r0 + min(gl, nr));   // lane l: start of row l (l <= nr)
+  const int e_end = __shfl_sync(gmask, my_ptr, nr, LPR);
+  int e0 = __shfl_sync(gmask, my_ptr, 0, LPR);
+  const size_t row_bytes = (size_t)a.row_vecs * 16;
+  const char* xb = reinterpret_cast<const char*>(a.x);
+  const float post = (MODE != kMean && a.scale) ? __ldg(a.scale) : 1.f;
+
+  bool act[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) act[i] = gl + i * LPR < a.row_vecs;
+  float acc[VPL][kVec];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) acc[i][k] = 0.f;
+
+  int cur = 0;                                            // row being accumulated (group-uniform)
+  int cur_beg = e0;
+  int cur_end = __shfl_sync(gmask, my_ptr, 1, LPR);
+
+  auto flush = [&]() {
+    char* ob = reinterpret_cast<char*>(a.out) + (size_t)(r0 + cur) * row_bytes + (size_t)gl * 16;
+    if (MODE == kMean) {
+      const float cntf = (float)max(cur_end - cur_beg, 1);
+      if (gl == 0 && a.inv_deg_out) a.inv_deg_out[r0 + cur] = __fdiv_rn(1.f, cntf);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) acc[i][k] = __fdiv_rn(acc[i][k], cntf);   // sum / count (IEEE)
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (act[i]) {
+        if (MODE != kMean) {
+#pragma unroll
+          for (int k = 0; k < kVec; ++k) acc[i][k] *= post;
+          if (a.accumulate) {
+            float f[kVec];
+            Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)i * LPR * 16), f);
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
+          }
+        }
+        stg_stream(ob + (size_t)i * LPR * 16, Elem<T>::pack(acc[i]));
+      }
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) acc[i][k] = 0.f;
+    }
+    ++cur;
+    cur_beg = cur_end;
+    cur_end = __shfl_sync(gmask, my_ptr, min(cur + 1, nr), LPR);
+  };
+
+  // index pipeline: c / wgt of the current chunk are ready; the next chunk's are in flight
+  auto load_idx = [&](int e, int& c, int& aux) {
+    c = 0; aux = 0;
+    if (e < e_end) {
+      c = ldg_stream(a.col + e);
+      if (MODE == kEdgeCoef) aux = ldg_stream(a.eid + e);
+    }
+  };
+  auto load_wgt = [&](int e, int c, int aux) -> float {
+    if (e >= e_end) return 0.f;
+    if (MODE == kNbrScale) return a.nbr_scale ? __ldg(a.nbr_scale + c) : 1.f;
+    if (MODE == kEdgeCoef) return __ldg(a.coef + aux);
+    return 1.f;
+  };
+  int c_cur, aux_cur, c_nxt, aux_nxt;
+  load_idx(e0 + gl, c_cur, aux_cur);
+  float w_cur = load_wgt(e0 + gl, c_cur, aux_cur);
+  load_idx(e0 + LPR + gl, c_nxt, aux_nxt);
+
+  while (e0 < e_end) {
+    const int cnt = min(LPR, e_end - e0);
+    // issue the dependent weight lookup of the next chunk and the ids of the one after it
+    const float w_nxt = (MODE == kMean) ? 1.f : load_wgt(e0 + LPR + gl, c_nxt, aux_nxt);
+    int c_nn, aux_nn;
+    load_idx(e0 + 2 * LPR + gl, c_nn, aux_nn);
+
+    for (int t = 0; t < cnt; t += kUnroll) {
+      uint4 v[kUnroll][VPL];
+      float wv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int cu = __shfl_sync(gmask, c_cur, t + u, LPR);
+        if (MODE != kMean) wv[u] = __shfl_sync(gmask, w_cur, t + u, LPR);
+        if (t + u < cnt) {
+          const char* rp = xb + (size_t)cu * row_bytes + (size_t)gl * 16;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i)
+            if (act[i]) v[u][i] = ldg_row(rp + (size_t)i * LPR * 16);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (t + u < cnt) {
+          const int e = e0 + t + u;
+          while (e >= cur_end) flush();                     // group-uniform: close finished rows
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            if (act[i]) {
+              float f[kVec];
+              Elem<T>::unpack(v[u][i], f);
+#pragma unroll
+              for (int k = 0; k < kVec; ++k) {
+                if (MODE == kMean)
+                  acc[i][k] = __fadd_rn(acc[i][k], f[k]);   // plain adds, CSR order: bit-exact
+                else
+                  acc[i][k] = fmaf(wv[u], f[k], acc[i][k]);
+              }
+            }
+          }
+        }
+      }
+    }
+    e0 += LPR;
+    c_cur = c_nxt; aux_cur = aux_nxt; w_cur = w_nxt;
+    c_nxt = c_nn; aux_nxt = aux_nn;
+  }
+  while (cur < nr) flush();                                 // last row and trailing empty rows
+}
+
 template <typename T, int MODE>
 int launch_gather(const GatherArgs& a, cudaStream_t st) {
   if (a.n_rows == 0) return TRG_OK;
@@ -150,19 +288,25 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
     const int64_t grid = ceil_div<int64_t>(a.n_rows, kThreads / LPR);                     \
     gather_reduce<T, LPR, VPL, MODE><<<(unsigned)grid, kThreads, 0, st>>>(a);             \
   }
+#define TRG_GATHER_SEG(LPR, VPL, R)                                                       \
+  {                                                                                       \
+    const int64_t grid = ceil_div<int64_t>(a.n_rows, (int64_t)(kThreads / LPR) * R);      \
+    gather_reduce_seg<T, LPR, VPL, MODE, R><<<(unsigned)grid, kThreads, 0, st>>>(a);      \
+  }
   if (rv <= 1) TRG_GATHER_CASE(1, 1)
   else if (rv <= 2) TRG_GATHER_CASE(2, 1)
   else if (rv <= 4) TRG_GATHER_CASE(4, 1)
-  else if (rv <= 8) TRG_GATHER_CASE(8, 1)
-  else if (rv <= 16) TRG_GATHER_CASE(16, 1)
-  else if (rv <= 32) TRG_GATHER_CASE(32, 1)
-  else if (rv <= 64) TRG_GATHER_CASE(32, 2)
-  else if (rv <= 128) TRG_GATHER_CASE(32, 4)
+  else if (rv <= 8) TRG_GATHER_SEG(8, 1, 4)
+  else if (rv <= 16) TRG_GATHER_SEG(16, 1, 8)
+  else if (rv <= 32) TRG_GATHER_SEG(32, 1, 8)
+  else if (rv <= 64) TRG_GATHER_SEG(32, 2, 8)
+  else if (rv <= 128) TRG_GATHER_SEG(32, 4, 8)
   else {
     set_error("gather: rows wider than 2048 bytes are not supported (row_vecs=%d)", rv);
     return TRG_E_UNSUPPORTED;
   }
 #undef TRG_GATHER_CASE
+#undef TRG_GATHER_SEG
   count_launch();
   TRG_LAUNCH_OK();
   return TRG_OK;
