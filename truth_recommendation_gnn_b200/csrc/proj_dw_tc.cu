@@ -216,17 +216,8 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
         for (int t = -1; t < p.n_terms; ++t) {
           const int off = t < 0 ? 0 : term_off[t];
           const int bytes = t < 0 ? C::kDzBytes : (p.term_n[t] / C::kElemsPerChunk) * C::kChunkBytes;
-          float4* hi = reinterpret_cast<float4*>(sb + off);
-          float4* lo = reinterpret_cast<float4*>(sb + off + bytes);
-          for (int i = tid; i < bytes / 16; i += 128) {
-            const float4 v = hi[i];
-            float4 h, l;
-            h.x = tf32_rna_dw(v.x); h.y = tf32_rna_dw(v.y); h.z = tf32_rna_dw(v.z); h.w = tf32_rna_dw(v.w);
-            l.x = tf32_rna_dw(v.x - h.x); l.y = tf32_rna_dw(v.y - h.y);
-            l.z = tf32_rna_dw(v.z - h.z); l.w = tf32_rna_dw(v.w - h.w);
-            hi[i] = h;
-            lo[i] = l;
-          }
+          const uint32_t hi = smem_u32(sb + off), lo = hi + (uint32_t)bytes;
+          for (int i = tid; i < bytes / 16; i += 128) split_tf32_16B(hi + (uint32_t)i * 16u, lo + (uint32_t)i * 16u);
         }
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&ready[stage]));

@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(Cfg<F32, BN>::kThreads, 1)
               mbar_arrive_expect_tx(fb, C::kTxBytes);
               tma_load_2d(smem_u32(stage_a_hi(stage)), &p.a_map[t], fb, kb * C::kElemsPerKBlock,
                           (int)(tile * BM));
+              // the same k-block of this CTA's NEXT tile: start its DRAM fetch into L2 now
+              if (nb == p.n_nblk - 1 && tile + gridDim.x < n_tiles)
+                tma_prefetch_l2_2d(&p.a_map[t], kb * C::kElemsPerKBlock, (int)((tile + gridDim.x) * BM));
               tma_load_2d(smem_u32(stage_b_hi(stage)), &p.b_hi_map, fb, kbt * C::kElemsPerKBlock,
                           nb * BN);
               if (F32)
@@ -187,18 +190,10 @@ __global__ void __launch_bounds__(Cfg<F32, BN>::kThreads, 1)
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int it = 0; it < p.n_nblk * p.total_kblocks; ++it) {
         mbar_wait(smem_u32(&full[stage]), phase);
-        float4* hi = reinterpret_cast<float4*>(stage_a_hi(stage));
-        float4* lo = reinterpret_cast<float4*>(stage_a_lo(stage));
+        const uint32_t hi = smem_u32(stage_a_hi(stage)) + (uint32_t)tid * 16u;
+        const uint32_t lo = smem_u32(stage_a_lo(stage)) + (uint32_t)tid * 16u;
 #pragma unroll
-        for (int i = 0; i < kABytes / 16 / 128; ++i) {
-          const float4 v = hi[i * 128 + tid];
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y);
-          l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          hi[i * 128 + tid] = h;
-          lo[i * 128 + tid] = l;
-        }
+        for (int i = 0; i < kABytes / 16 / 128; ++i) split_tf32_16B(hi + i * 2048u, lo + i * 2048u);
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&ready[stage]));
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }

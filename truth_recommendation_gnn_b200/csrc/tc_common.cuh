@@ -47,6 +47,32 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- 128-bit shared-memory access by 32-bit shared address (LDS.128 / STS.128, not generic LD/ST) ----
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+// 3xTF32 operand split of one 16-byte vector, in place: hi = x with the 13 low mantissa bits
+// cleared (exactly a tf32 value, whatever the tensor core does with low bits), lo = x - hi (exact in
+// fp32, < 2^-10 |x|; the tensor core keeps its top 11 significant bits -> 2^-21 relative).  Two ALU
+// ops per element: cvt.rna.tf32 is emulated with ~8 and made the split warps the bottleneck.
+__device__ __forceinline__ void split_tf32_16B(uint32_t hi_addr, uint32_t lo_addr) {
+  const uint4 v = lds128(hi_addr);
+  uint4 h, l;
+  h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+  l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+  l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+  l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+  l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+  sts128(hi_addr, h);
+  sts128(lo_addr, l);
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -58,6 +84,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint3
       "%4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a 2-D box (no shared-memory destination, no barrier): lets the DRAM latency of
+// tiles needed one tile-time later overlap the current tile without holding a ring slot.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0,
                                             int c1, int c2) {
