@@ -263,11 +263,13 @@ def gpu_train_bench(args, w, rank, world, dev):
                 setup_s=setup_s, h2d=h2d, d2h=4 * world, mem_gb=torch.cuda.max_memory_allocated(dev) / 2**30)
 
 
-def gpu_topk_bench(args, dev, n_post, hidden, k=100, batch=4096, iters=3):
-    """Secondary metric: top-k recs/s (inference.py:427-428 batched; BASELINE config 5 shape)."""
+def gpu_topk_bench(args, dev, n_post=50_000_000, hidden=128, k=100, batch=4096, iters=3):
+    """Secondary metric: top-k recs/s -- inference.py:427-428 batched, BASELINE config 5 shape (score all
+    50M posts per user batch of 4096, top-100; bf16 in, fp32 accumulate; tcgen05 + warp-level select)."""
     import truth_recommendation_gnn_b200 as trg
     from truth_recommendation_gnn_b200 import synth
-    q, cat = synth.synth_queries(batch, n_post, hidden, device=dev)
+    q, cat = synth.synth_queries(batch, n_post, hidden, device=dev, dtype=torch.bfloat16)
+    q_host = q.cpu().pin_memory()
     trg.score_topk(q, cat, k)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -277,9 +279,20 @@ def gpu_topk_bench(args, dev, n_post, hidden, k=100, batch=4096, iters=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    # end to end: the query batch comes from pinned host memory, ids + scores go back to the host
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        v, i = trg.score_topk(q_host.to(dev, non_blocking=True), cat, k)
+        v, i = v.cpu(), i.cpu()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / iters
+    pk = peaks()
+    tf = 2.0 * batch * n_post * hidden / ms / 1e9
     return dict(users_per_s=batch / ms * 1e3, recs_per_s=batch * k / ms * 1e3, ms_per_batch=ms,
-                tflops=2.0 * batch * n_post * hidden / ms / 1e9, batch=batch, n_post=n_post, hidden=hidden, k=k,
-                dtype="f32", kernel="score_topk_f32 (SIMT fp32 FMA)")
+                e2e_recs_per_s=batch * k / ms_e2e * 1e3, e2e_ms_per_batch=ms_e2e,
+                roofline=dict(bound="tensor", achieved=tf, peak=pk["bf16_tflops"], unit="TFLOP/s",
+                              frac=tf / pk["bf16_tflops"], peak_source=pk["source"]),
+                batch=batch, n_post=n_post, hidden=hidden, k=k, dtype="bf16 in / fp32 accumulate",
+                kernel="score_topk_tc_kernel (tcgen05 kind::f16 + TMEM row scan + warp-cooperative top-k merge)")
 
 
 def main():
@@ -355,8 +368,8 @@ def main():
             "setup_s": round(r["setup_s"], 2), "peak_mem_gb": round(r["mem_gb"], 2),
         }
         if not args.no_topk and world == 1:
-            npost = w["num_posts"] if w["num_posts"] <= 5_000_000 else 5_000_000
-            line["topk"] = gpu_topk_bench(args, dev, npost, w["hidden"], k=100, batch=4096)
+            torch.cuda.empty_cache()
+            line["topk"] = gpu_topk_bench(args, dev)
         if not args.no_cpu_baseline and world == 1:
             cb = run_cpu_oracle(w, 3, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

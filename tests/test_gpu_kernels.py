@@ -293,6 +293,32 @@ def test_score_topk_integer_exact(dev, b, p, h, k):
     assert torch.equal(gi2.cpu(), ids + 1000)
 
 
+@pytest.mark.parametrize("b,p,h,k", [(1, 20_000, 64, 10), (300, 50_000, 128, 100), (129, 7001, 256, 100), (70, 9000, 192, 100),
+                                     (4096, 3000, 128, 100), (5, 7, 64, 10), (64, 200_000, 128, 100)])
+def test_score_topk_bf16_tensor_core_integer_exact(dev, b, p, h, k):
+    """bf16 tcgen05 path: small-integer embeddings are exact in bf16 and their dot products exact in
+    the fp32 accumulator, so values and ids (with massive ties) must match the oracle bit for bit."""
+    g = torch.Generator().manual_seed(b * p + h)
+    q = torch.randint(0, 4, (b, h), generator=g).float()
+    cat = torch.randint(0, 3, (p, h), generator=g).float()
+    cat[torch.rand(p, generator=g) < 0.05] = 0
+    vals, ids = otopk.score_topk(q, cat, k)
+    gv, gi = trg.score_topk(q.to(dev).bfloat16(), cat.to(dev).bfloat16(), k, id_offset=7)
+    assert torch.equal(gv.cpu(), vals) and torch.equal(gi.cpu(), ids + 7)
+
+
+def test_score_topk_bf16_random(dev):
+    q, cat = synth.synth_queries(200, 100_000, 128, zero_frac=0.05)
+    qb, cb = q.bfloat16(), cat.bfloat16()
+    scores = qb.float() @ cb.float().t()                 # fp32 oracle on bf16-rounded inputs
+    vals, ids = otopk.topk_canonical(scores, 100)
+    gv, gi = trg.score_topk(qb.to(dev), cb.to(dev), 100)
+    assert_close(gv.cpu(), vals, 1e-5, "bf16 top-k values (fp32 accumulate)")
+    s_at = scores.gather(1, gi.cpu())
+    assert_close(s_at, gv.cpu(), 1e-5, "scores at returned ids")
+    assert (gi.cpu() == ids).float().mean() > 0.99       # only near-ties may swap
+
+
 def test_score_topk_float_and_sharded(dev):
     q, cat = synth.synth_queries(50, 30_000, 64, zero_frac=0.05)
     scores = q @ cat.t()

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < n_kblocks; ++kb) {
-        mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+        mbar_wait_backoff(smem_u32(&empty[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full[stage]);
         unsigned char* sb = smem + (size_t)stage * stage_bytes;
         const int r = (int)(row0 + (long long)kb * C::KR);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
       uint32_t phase = 0;
       const uint32_t lbo = C::kChunkBytes;   // between 128-byte column chunks
       for (int kb = 0; kb < n_kblocks; ++kb) {
-        mbar_wait(smem_u32(F32 ? &ready[stage] : &full[stage]), phase);
+        mbar_wait_backoff(smem_u32(F32 ? &ready[stage] : &full[stage]), phase);
         tc_fence_after();
         unsigned char* sb = smem + (size_t)stage * stage_bytes;
         const uint32_t dz_hi = smem_u32(sb), dz_lo = smem_u32(sb + C::kDzBytes);

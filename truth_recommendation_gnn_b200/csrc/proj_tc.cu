@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(Cfg<F32, BN>::kThreads, 1)
           int kbt = 0;
           for (int t = 0; t < p.n_a; ++t) {
             for (int kb = 0; kb < p.a_kblocks[t]; ++kb, ++kbt) {
-              mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+              mbar_wait_backoff(smem_u32(&empty[stage]), phase ^ 1);
               const uint32_t fb = smem_u32(&full[stage]);
               mbar_arrive_expect_tx(fb, C::kTxBytes);
               tma_load_2d(smem_u32(stage_a_hi(stage)), &p.a_map[t], fb, kb * C::kElemsPerKBlock,
@@ -149,11 +149,11 @@ __global__ void __launch_bounds__(Cfg<F32, BN>::kThreads, 1)
       uint32_t phase = 0, acc_phase = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int nb = 0; nb < p.n_nblk; ++nb) {
-          mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+          mbar_wait_backoff(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.total_kblocks; ++kb) {
-            mbar_wait(smem_u32(F32 ? &ready[stage] : &full[stage]), phase);
+            mbar_wait_backoff(smem_u32(F32 ? &ready[stage] : &full[stage]), phase);
             tc_fence_after();
             const uint64_t a_hi = make_smem_desc_sw128(smem_u32(stage_a_hi(stage)), 0, 1024);
             const uint64_t b_hi = make_smem_desc_sw128(smem_u32(stage_b_hi(stage)), 0, 1024);

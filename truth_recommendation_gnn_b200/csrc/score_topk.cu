@@ -233,6 +233,13 @@ int choose_splits(int64_t n_query, int64_t n_cat, int64_t* tiles_per_split) {
 }
 
 }  // namespace
+namespace tc {
+bool score_tc_eligible(int hidden, int dtype, int k);
+size_t score_tc_workspace_bytes(int64_t n_query, int64_t n_cat, int hidden, int k);
+int score_topk_tc(const void* q, const void* cat, int64_t n_query, int64_t n_cat, int hidden, int k,
+                  int64_t id_offset, float* vals_out, int64_t* ids_out, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+}  // namespace tc
 }  // namespace trg
 
 using namespace trg;
@@ -243,8 +250,13 @@ extern "C" size_t trg_score_topk_workspace_bytes(int64_t n_query, int64_t n_cat,
   int64_t tps;
   const int splits = choose_splits(n_query, n_cat, &tps);
   const int64_t kk = std::min<int64_t>(k, n_cat);
-  return align_up((size_t)n_query * splits * kk * 4, 256) +
-         align_up((size_t)n_query * splits * kk * 8, 256);
+  const size_t simt = align_up((size_t)n_query * splits * kk * 4, 256) +
+                      align_up((size_t)n_query * splits * kk * 8, 256);
+  // dtype is not part of this query: size for whichever kernel (fp32 FMA / bf16 tcgen05) needs more
+  size_t tcb = 0;
+  if (hidden % 64 == 0 && hidden <= 256 && kk <= 128)
+    tcb = tc::score_tc_workspace_bytes(n_query, n_cat, hidden, (int)kk);
+  return std::max(simt, tcb);
 }
 
 extern "C" int trg_topk_merge(const float* vals_in, const int64_t* ids_in, int64_t n_query,
@@ -275,9 +287,17 @@ extern "C" int trg_score_topk(const void* q, const void* cat, int64_t n_query, i
   TRG_CHECK_ARG(((uintptr_t)q | (uintptr_t)cat) % 16 == 0, "trg_score_topk: tables must be 16-byte aligned");
   const int kk = (int)std::min<int64_t>(k, n_cat);
   TRG_CHECK_ARG(kk <= kMaxK, "trg_score_topk: k=%d > %d is not supported", kk, kMaxK);
+  if (dtype == TRG_BF16) {
+    if (!tc::score_tc_eligible(hidden, dtype, kk)) {
+      set_error("trg_score_topk(bf16): hidden=%d k=%d unsupported: hidden must be in {64,128,192,256}, k <= 128, and the query block (256*hidden B) + the per-row lists (1 KiB*k) + two catalogue stages must fit in 227 KiB of shared memory", hidden, kk);
+      return TRG_E_UNSUPPORTED;
+    }
+    return tc::score_topk_tc(q, cat, n_query, n_cat, hidden, kk, id_offset, vals_out, ids_out, workspace,
+                             workspace_bytes, st);
+  }
   if (dtype != TRG_F32) {
-    set_error("trg_score_topk: dtype %d not supported by this build", dtype);
-    return TRG_E_UNSUPPORTED;
+    set_error("trg_score_topk: unknown dtype %d", dtype);
+    return TRG_E_ARG;
   }
   TRG_CHECK_ARG(hidden > 0 && hidden % 4 == 0 && hidden <= 256,
                 "trg_score_topk(fp32): hidden=%d must be a multiple of 4 and <= 256", hidden);

@@ -42,6 +42,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait used by the single-thread producer / MMA-issuer roles: back off between polls so the spin does
+// not steal issue slots from the compute warps that share the SM sub-partition (ncu showed ~60 polls
+// per tile from each role thread).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
