@@ -18,7 +18,6 @@
 // Tensor-bound: 2*B*P*H flops against 2*P*H bytes of catalogue (AI = B = 4096 flop/B).
 #include <algorithm>
 #include <cfloat>
-#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -34,7 +33,6 @@ struct ScoreTcParams {
   long long n_query, n_cat, id_offset;
   long long tiles_per_split;
   int k, n_splits, kblocks;   // kblocks = H / 64
-  int dbg;
   int* thr_shared;            // [B] ordered-int keys of the best published K-th score per query row
   float* part_vals;           // [B][n_splits][k]
   long long* part_ids;        // [B][n_splits][k]
@@ -434,7 +432,6 @@ int score_topk_tc(const void* q, const void* cat, int64_t n_query, int64_t n_cat
   if (rc) return rc;
   rc = make_tmap_2d(&p.c_map, cat, TRG_BF16, (uint64_t)n_cat, hidden, hidden, cfg.ns);
   if (rc) return rc;
-  { const char* e = getenv("TRG_DEBUG_TOPK"); p.dbg = e ? atoi(e) : 0; }
   p.n_query = n_query; p.n_cat = n_cat; p.id_offset = id_offset; p.k = k; p.kblocks = hidden / 64;
   p.n_splits = score_tc_splits(n_query, n_cat, hidden, k, &p.tiles_per_split);
   p.part_vals = reinterpret_cast<float*>(ws);
