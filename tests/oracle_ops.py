@@ -9,7 +9,18 @@ from oracle import topk as otopk
 
 class OracleOps:
     @staticmethod
+    def gather_sum(rel, which, x):
+        ei = rel.edge_index
+        if which == "fwd":
+            return torch.zeros(rel.n_dst, x.size(1), dtype=x.dtype).index_add_(0, ei[1], x[ei[0]])
+        return torch.zeros(rel.n_src, x.size(1), dtype=x.dtype).index_add_(0, ei[0], x[ei[1]])
+
+    @staticmethod
     def aggregate(x_src, rel):
+        from truth_recommendation_gnn_b200.collectives import PushMeanAggFn
+        from truth_recommendation_gnn_b200.graph import PushRelation
+        if isinstance(rel, PushRelation):      # host logic under test; the oracle supplies the primitive
+            return PushMeanAggFn.apply(x_src, rel, OracleOps.gather_sum, False)
         ei = rel.edge_index
         return osage.scatter_mean(x_src.index_select(0, ei[0]), ei[1], rel.n_dst)[0]
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from .graph import RelationGraph
+from .graph import PushRelation, RelationGraph
 from .nn import CUDA_OPS, REL_DIRECT, REL_ENGAGE, REL_SOCIAL, StackedWeightedRGCN, WeightedRGCN
 
 
@@ -24,45 +24,7 @@ def chunk_of(n: int, world: int) -> int:
     return (n + world - 1) // world
 
 
-# ------------------------------------------------------------------------------------------
-# collectives with autograd
-# ------------------------------------------------------------------------------------------
-def _all_gather_rows(x_local: torch.Tensor, group=None) -> torch.Tensor:
-    world = dist.get_world_size(group)
-    out = torch.empty(world * x_local.size(0), *x_local.shape[1:], dtype=x_local.dtype, device=x_local.device)
-    dist.all_gather_into_tensor(out, x_local.contiguous(), group=group)
-    return out
-
-
-def _reduce_scatter_rows(g_full: torch.Tensor, group=None) -> torch.Tensor:
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    chunk = g_full.size(0) // world
-    g_full = g_full.contiguous()
-    if dist.get_backend(group) == "gloo":      # gloo has no reduce_scatter: all_reduce + slice
-        dist.all_reduce(g_full, group=group)
-        return g_full[rank * chunk:(rank + 1) * chunk].clone()
-    out = torch.empty(chunk, *g_full.shape[1:], dtype=g_full.dtype, device=g_full.device)
-    dist.reduce_scatter_tensor(out, g_full, op=dist.ReduceOp.SUM, group=group)
-    return out
-
-
-class AllGatherRows(torch.autograd.Function):
-    """[chunk, F] per rank -> [world*chunk, F]; backward = reduce-scatter (sum) of the partials."""
-
-    @staticmethod
-    def forward(ctx, x_local):
-        return _all_gather_rows(x_local)
-
-    @staticmethod
-    def backward(ctx, g_full):
-        return _reduce_scatter_rows(g_full)
-
-
-def all_gather_rows(x_local):
-    if x_local.requires_grad:
-        return AllGatherRows.apply(x_local)
-    return _all_gather_rows(x_local)
+from .collectives import all_gather_rows, all_gather_rows_raw as _all_gather_rows  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------
@@ -94,6 +56,18 @@ class ShardedGraph:
         self.n_local_edges = {}
         for rel in (REL_DIRECT, REL_SOCIAL, REL_ENGAGE):
             ei = edge_index_dict[rel]
+            if rel == REL_DIRECT and self.world > 1:
+                # post -> user is partitioned by SOURCE: partial sums for all users are pushed to
+                # their owners (U x H moves instead of an all-gather of the 5x larger post table)
+                a, b, c = n_of["post"]
+                m = (ei[0] >= a) & (ei[0] < b)
+                loc = torch.stack([ei[0][m] - a, ei[1][m]]).contiguous()
+                deg = torch.bincount(ei[1], minlength=num_users)[self.u0:self.u1].float()
+                inv = torch.ones(self.cu, device=ei.device)
+                inv[:deg.numel()] = 1.0 / deg.clamp(min=1.0)
+                self.rels[rel] = PushRelation(RelationGraph(loc, c, self.cu * self.world), inv)
+                self.n_local_edges[rel] = int(loc.size(1))
+                continue
             a, b, c = n_of[rel[2]]
             m = (ei[1] >= a) & (ei[1] < b)
             loc = torch.stack([ei[0][m], ei[1][m] - a]).contiguous()
@@ -115,7 +89,7 @@ class ShardedGraph:
     def layer0_sources(self):
         """Input features are static: gather them once (train_gnn.py:211 moves the graph once)."""
         if self._layer0_src is None:
-            self._layer0_src = {t: _all_gather_rows(x) for t, x in self.x_local.items()}
+            self._layer0_src = {"user": _all_gather_rows(self.x_local["user"]), "post": self.x_local["post"]}
         return self._layer0_src
 
 
@@ -124,7 +98,8 @@ def forward_sharded(model, shard: ShardedGraph, ops=CUDA_OPS):
     layers = list(model.layers) if isinstance(model, StackedWeightedRGCN) else [model]
     dst = shard.x_local
     for i, layer in enumerate(layers):
-        src = shard.layer0_sources() if i == 0 else {t: all_gather_rows(x) for t, x in dst.items()}
+        # only the user table is gathered: posts are consumed where they live (PushRelation)
+        src = shard.layer0_sources() if i == 0 else {"user": all_gather_rows(dst["user"]), "post": dst["post"]}
         dst = layer.forward_partitioned(src, dst, shard.rels, ops)
     return dst
 

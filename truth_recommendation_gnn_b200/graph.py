@@ -87,6 +87,16 @@ class RelationGraph:
         return self._bwd
 
 
+class PushRelation:
+    """A relation partitioned by SOURCE on multi-GPU runs (see collectives.PushMeanAggFn): ``rel``
+    holds this rank's edges as (local source id, global destination id); ``inv_deg`` is 1 / max(global
+    in-degree, 1) of the destination rows this rank owns."""
+
+    def __init__(self, rel: RelationGraph, inv_deg: torch.Tensor):
+        self.rel = rel
+        self.inv_deg = inv_deg
+
+
 class GraphCache:
     """LRU cache keyed on ``(data_ptr, shape, _version, n_src, n_dst)``."""
 

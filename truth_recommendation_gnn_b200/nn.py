@@ -20,7 +20,7 @@ from torch.nn.parameter import Parameter, UninitializedParameter
 
 from . import _lib
 from .functional import fused_projection, sage_mean_aggregate
-from .graph import relation_graph
+from .graph import PushRelation, relation_graph
 
 REL_DIRECT = ("post", "rev_engages", "user")
 REL_SOCIAL = ("user", "social", "user")
@@ -192,7 +192,17 @@ class CudaOps:
 
     @staticmethod
     def aggregate(x_src, rel):
+        if isinstance(rel, PushRelation):      # multi-GPU, source-partitioned relation
+            from .collectives import PushMeanAggFn
+            return PushMeanAggFn.apply(x_src, rel, CudaOps.gather_sum, True)
         return sage_mean_aggregate(x_src, rel, True)
+
+    @staticmethod
+    def gather_sum(rel, which, x):
+        """Plain segmented gather-sum over the forward ("fwd": rows = destinations) or transposed
+        ("bwd": rows = sources) CSR of a relation -- K2 without the 1/deg scale."""
+        from .functional import sage_agg_bwd
+        return sage_agg_bwd(rel.fwd if which == "fwd" else rel.bwd, None, x)
 
     @staticmethod
     def project(terms, bias, relu, scale_rels):
