@@ -37,9 +37,16 @@ def main():
                                    g.interaction_type_tensor, U, P, neg_p=neg)
             l_mod = tdist.train_step_sharded(mod, o_mod, shard, neg_p_global=neg)
             assert abs(l_ref - l_mod) <= tol * abs(l_ref), (str(dtype), s, l_ref, l_mod)
+            if s == 0:      # gradients of the first step (same weights on both sides)
+                for (n, a), (_, b) in zip(mod.named_parameters(), ref.named_parameters()):
+                    ga, gb = a.grad.detach().float(), b.grad.detach().float()
+                    err = float((ga - gb).abs().max() / gb.abs().max())
+                    assert err <= 10 * tol, ("grad", n, err)
+        # after 3 Adam steps: Adam normalises near-zero gradients to +-lr, so a tiny gradient
+        # difference can move a weight by a fraction of lr -- compare at lr scale, not at 1e-5
         for (n, a), (_, b) in zip(mod.named_parameters(), ref.named_parameters()):
-            err = float((a.float() - b.float()).abs().max() / b.float().abs().max())
-            assert err <= 10 * tol, (n, err)
+            err = float((a.detach().float() - b.detach().float()).abs().max())
+            assert err <= 1e-3 * 0.5 + 50 * tol * float(b.detach().float().abs().max()), (n, err)
         with torch.no_grad():
             full = ref(g.x_dict, g.edge_index_dict)
             loc = tdist.forward_sharded(mod, shard)
