@@ -35,4 +35,4 @@ PARITY PIN STATUS
   reference's call sites and on dense-adjacency math (``tests/test_oracle.py``), plus the
   committed fixtures under ``tests/golden/`` produced by ``tests/golden/make_golden.py``.
 """
-from . import csr, sage, topk  # noqa: F401
+from . import csr, sage, topk  # noqa: F401  (oracle.evaluate needs sklearn: imported on demand)

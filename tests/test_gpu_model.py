@@ -157,3 +157,41 @@ def test_multi_layer_needs_transposed_backward(dev):
     trg.link_bce_loss(o["user"], o["post"], gd.train_edge_index, neg.to(dev), gd.interaction_type_tensor, U).backward()
     for (n, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
         assert_close(a.grad.cpu(), b.grad, 5 * TOL_F32, f"grad {n}")
+
+
+def test_batched_evaluate_matches_reference_loop(dev):
+    """§8f N1: one K5 launch + device ops == the per-user python/sklearn loop (train_gnn.py:290-367)."""
+    from oracle import evaluate as oeval
+    U, P, H, T = 300, 900, 64, 1500
+    g = torch.Generator().manual_seed(5)
+    user_emb = torch.relu(torch.randn(U, H, generator=g))
+    post_emb = torch.relu(torch.randn(P, H, generator=g))
+    tu = torch.randint(0, U, (T,), generator=g)
+    tp = torch.randint(0, 400, (T,), generator=g) + U                 # global post ids, subset as candidates
+    test_edges = torch.stack([torch.cat([tu, tu[:40]]), torch.cat([tp, tp[:40]])])   # duplicate test edges
+    for K in (10, 3):
+        r_ref, n_ref = oeval.evaluate(test_edges, user_emb, post_emb, U, K)
+        r, n = trg.evaluate(test_edges.to(dev), user_emb.to(dev), post_emb.to(dev), K=K, num_users=U)
+        assert abs(r - r_ref) < 1e-9 and abs(n - n_ref) < 1e-6, (K, r, r_ref, n, n_ref)
+
+
+def test_cold_start_batch_matches_per_user_forward(dev):
+    """§8f N2: batched cold-start embedding + top-k == the 1-node / 0-edge forward per user."""
+    sd = synth.init_state_dict(64, 64)
+    ref = oracle_model(64, 1, sd)
+    model = _gpu_model(64, 1, sd, dev).eval()
+    g = torch.Generator().manual_seed(9)
+    feats = torch.zeros(33, 64)
+    feats[:, :3] = torch.rand(33, 3, generator=g) * 3
+    _, cat = synth.synth_queries(1, 4000, 64)
+    empty = torch.empty(2, 0, dtype=torch.long)
+    eid = {osage.REL_DIRECT: empty, osage.REL_SOCIAL: empty, osage.REL_ENGAGE: empty}
+    emb = trg.embed_cold_users(model, feats.to(dev))
+    vals, ids = trg.recommend_cold_users(model, feats.to(dev), cat.to(dev), k=10)
+    for i in range(33):
+        with torch.no_grad():
+            e = ref({"user": feats[i:i + 1], "post": torch.empty(0, 64)}, eid)["user"]
+        assert_close(emb[i:i + 1].cpu(), e, TOL_F32, "cold-start embedding")
+        ev, ei = otopk.score_topk(e, cat, 10)
+        assert_close(vals[i:i + 1].cpu(), ev, TOL_F32, "cold-start scores")
+        assert torch.equal(ids[i:i + 1].cpu(), ei)

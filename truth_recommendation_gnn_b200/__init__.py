@@ -10,6 +10,7 @@ from .functional import (link_bce_loss, sage_mean_aggregate, score_topk, topk_me
 from .graph import CSR, RelationGraph, build_csr, clear_cache, relation_graph  # noqa: F401
 from .nn import (REL_DIRECT, REL_ENGAGE, REL_SOCIAL, Linear, SAGEConv, StackedWeightedRGCN,  # noqa: F401
                  WeightedRGCN)
+from .evaluation import embed_cold_users, evaluate, recommend_cold_users  # noqa: F401
 from .train import recommend, train_step  # noqa: F401
 
 __version__ = "0.1.0"
