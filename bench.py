@@ -192,7 +192,7 @@ def gpu_train_bench(args, w, rank, world, dev):
         # destination partition: this rank keeps its rows / edges and drops the full graph
         shard = tdist.ShardedGraph(g.x_dict, g.edge_index_dict, g.train_edge_index,
                                    g.interaction_type_tensor, U, P)
-        negs = [synth.synth_neg(P, Ee, i, device=dev)[shard.pos_mask].contiguous() for i in range(n_host)]
+        negs = [shard.local_negatives(synth.synth_neg(P, Ee, i, device=dev)) for i in range(n_host)]
         del g
         torch.cuda.empty_cache()
     else:

@@ -101,6 +101,18 @@ int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, const int32_
                      float* c_pos, float* c_neg, void* g_u,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-GPU form of K4: the loss terms are evaluated by the OWNER OF THE POST.  Rows = local posts
+ * (anchor table), one gathered row per edge from the all-gathered user table (5x smaller than the
+ * post table), one label per launch: label 1 = positive edges (loss += wbar * sum softplus(-x) / E),
+ * label 0 = sampled negatives (loss += sum softplus(x) / E); E = n_edges_scale, the global positive
+ * count.  loss_out[0] receives this launch's partial loss; coef_out[eid] = dloss/dx per edge;
+ * g_anchor (+)= sum_e coef_e * gathered[col_e] (accumulate != 0 adds to the rows already there). */
+int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                         const void* anchor, const void* gathered, int64_t n_rows,
+                         int64_t n_edges_scale, int32_t hidden, int dtype, int label,
+                         const float* wbar, float* loss_out, float* coef_out, void* g_anchor,
+                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- A3+A4 / K3: SAGE projections + relation combine + ReLU ---------------------------------
  * Replaces lin_l(mean) + lin_r(x_dst) of every SAGEConv and the combine of
  * train_gnn.py:187-198.  out = act( sum_i alpha_i * ( A_i[n, k_i] @ W_i[h, k_i]^T ) + bias ),

@@ -32,14 +32,36 @@ class OracleOps:
         return torch.relu(out) if relu else out
 
 
+class _Csr:
+    def __init__(self, other, key, n_rows):
+        self.other, self.key, self.n_rows = other, key, n_rows
+
+
 class OracleLossOps:
+    """Oracle primitives for dist.AnchoredLinkLossFn (post-owner loss partition)."""
+
     @staticmethod
-    def link_loss(user_local, post_full, shard, neg_local):
-        pu, pp = shard.train_local[0], shard.train_local[1]
-        pos = (user_local[pu] * post_full[pp]).sum(1)
-        neg = (user_local[pu] * post_full[neg_local]).sum(1)
-        e = float(shard.n_pos_global)
-        return shard.wbar[0] * F.softplus(-pos).sum() / e + F.softplus(neg).sum() / e
+    def csr(other, key, n_key, n_other):
+        return _Csr(other, key, n_key)
+
+    @staticmethod
+    def anchor_loss(csr, post_local, user_full, n_edges, label, wbar, want, g_post):
+        d = (post_local[csr.key] * user_full[csr.other]).sum(1)
+        z = -d if label else d
+        scale = float(wbar[0]) if label else 1.0
+        loss = (scale * F.softplus(z).sum() / n_edges).reshape(1)
+        if not want:
+            return loss.detach(), None, None
+        coef = (-scale if label else scale) * torch.sigmoid(z) / n_edges
+        g = torch.zeros_like(post_local).index_add_(0, csr.key, coef[:, None] * user_full[csr.other])
+        return loss.detach(), coef.detach(), (g if g_post is None else g_post + g).detach()
+
+    @staticmethod
+    def wsum(csr, coef, post_local, scale, out):
+        g = torch.zeros(csr.n_rows, post_local.size(1), dtype=post_local.dtype)
+        g.index_add_(0, csr.key, coef[:, None] * post_local[csr.other])
+        g = g * scale
+        return g if out is None else out + g
 
 
 def score_topk(q, cat, k, id_offset=0):

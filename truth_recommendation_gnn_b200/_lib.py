@@ -43,6 +43,8 @@ SIGNATURES = {
     "trg_edge_bce_workspace_bytes": (_sz, [_i64]),
     "trg_edge_bce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _sz, _vp]),
+    "trg_edge_anchor_loss": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _int, _vp, _vp, _vp,
+                                    _vp, _int, _vp, _sz, _vp]),
     "trg_sage_proj_workspace_bytes": (_sz, [_i32, _i32, _int]),
     "trg_sage_proj_fwd": (_int, [ctypes.POINTER(TrgProjTerm), _i32, _vp, _i64, _i32, _int, _int, _vp,
                                  _vp, _sz, _vp]),

@@ -28,6 +28,8 @@ struct BceArgs {
   int64_t n_users;
   float inv_e;
   int row_vecs;
+  int label;        // single-row mode: 1 = positives (softplus(-x), weight wbar), 0 = negatives
+  int accumulate;   // single-row mode: add to the existing anchor-gradient rows
 };
 
 __device__ __forceinline__ float softplus(float x) {  // log(1 + e^x), stable
@@ -42,10 +44,16 @@ __device__ __forceinline__ float sigmoid(float x) {
 // stream (same scheme as gather_reduce_seg): the (post id, edge id) pairs of the next 32-edge chunk
 // and the dependent neg_p[eid] lookup are prefetched two chunks / one chunk ahead, so the only
 // exposed latency is that of the post rows themselves (2 per edge, kUnroll edges in flight).
-template <typename T, int LPR, int VPL, int R>
+//
+// TWO = true : anchor rows = users, two gathered post rows per edge (positive + sampled negative):
+//              the single-GPU fused loss.
+// TWO = false: one gathered row per edge and a label per launch: the multi-GPU form, where the loss is
+//              evaluated by the OWNER OF THE POST (anchor rows = local posts, gathered rows = the
+//              all-gathered user table, which is 5x smaller than the post table).
+template <typename T, int LPR, int VPL, int R, bool TWO>
 __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const BceArgs a) {
   constexpr int kVec = Elem<T>::kVec;
-  constexpr int kUnroll = LPR < 8 ? (LPR >= 4 ? 2 : 1) : (VPL == 1 ? 4 : 2);
+  constexpr int kUnroll = (LPR < 8 ? (LPR >= 4 ? 2 : 1) : (VPL == 1 ? 4 : 2)) * (TWO ? 1 : 2);
   static_assert(R < LPR, "row boundaries are held one per lane");
   __shared__ double red[2][kThreads / 32];
   const int lane = threadIdx.x & 31;
@@ -87,7 +95,15 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
         char* ob = reinterpret_cast<char*>(a.g_u) + (size_t)(r0 + cur) * row_bytes;
 #pragma unroll
         for (int i = 0; i < VPL; ++i)
-          if (act[i]) stg_stream(ob + (size_t)(gl + i * LPR) * 16, Elem<T>::pack(ga[i]));
+          if (act[i]) {
+            if (!TWO && a.accumulate) {
+              float f[kVec];
+              Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)(gl + i * LPR) * 16), f);
+#pragma unroll
+              for (int k = 0; k < kVec; ++k) ga[i][k] += f[k];
+            }
+            stg_stream(ob + (size_t)(gl + i * LPR) * 16, Elem<T>::pack(ga[i]));
+          }
       }
       ++cur;
       cur_end = __shfl_sync(gmask, my_ptr, min(cur + 1, nr), LPR);
@@ -112,13 +128,13 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
     // (A bulk L2 prefetch of the next chunk's rows was measured SLOWER: 13.5 vs 12.7 ms at cfg 2.)
     int cp_cur, id_cur, cn_cur = 0, cp_nxt, id_nxt;
     load_idx(e0 + gl, cp_cur, id_cur);
-    if (e0 + gl < e_end) cn_cur = (int)ldg_stream(a.neg_p + id_cur);
+    if (TWO && e0 + gl < e_end) cn_cur = (int)ldg_stream(a.neg_p + id_cur);
     load_idx(e0 + LPR + gl, cp_nxt, id_nxt);
 
     while (e0 < e_end) {
       const int cnt = min(LPR, e_end - e0);
       int cn_nxt = 0;
-      if (e0 + LPR + gl < e_end) cn_nxt = (int)ldg_stream(a.neg_p + id_nxt);
+      if (TWO && e0 + LPR + gl < e_end) cn_nxt = (int)ldg_stream(a.neg_p + id_nxt);
       int cp_nn, id_nn;
       load_idx(e0 + 2 * LPR + gl, cp_nn, id_nn);
       float my_cpos = 0.f, my_cneg = 0.f;
@@ -138,13 +154,13 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
             for (int i = 0; i < VPL; ++i)
               if (act[i]) {
                 vp[q][i] = ldg_row(pb + (size_t)cpq * row_bytes + (size_t)(gl + i * LPR) * 16);
-                vn[q][i] = ldg_row(pb + (size_t)cnq * row_bytes + (size_t)(gl + i * LPR) * 16);
+                if (TWO) vn[q][i] = ldg_row(pb + (size_t)cnq * row_bytes + (size_t)(gl + i * LPR) * 16);
               }
           }
         }
         // partial dots, then ONE halving butterfly over the group: afterwards each lane holds the
         // group total of one of the 2*kUnroll scores (value j on lanes [j*LPR/NV, (j+1)*LPR/NV))
-        constexpr int NV = 2 * kUnroll;
+        constexpr int NV = TWO ? 2 * kUnroll : kUnroll;
         static_assert(LPR >= NV, "transpose-reduce needs at least one lane per value");
         float v[NV];
 #pragma unroll
@@ -156,17 +172,21 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
               if (act[i]) {
                 float fp[kVec], fn[kVec];
                 Elem<T>::unpack(vp[q][i], fp);
-                Elem<T>::unpack(vn[q][i], fn);
+                if (TWO) Elem<T>::unpack(vn[q][i], fn);
 #pragma unroll
                 for (int k = 0; k < kVec; ++k) {
                   dp = fmaf(uf[i][k], fp[k], dp);
-                  dn = fmaf(uf[i][k], fn[k], dn);
+                  if (TWO) dn = fmaf(uf[i][k], fn[k], dn);
                 }
               }
             }
           }
-          v[2 * q] = dp;
-          v[2 * q + 1] = dn;
+          if (TWO) {
+            v[2 * q] = dp;
+            v[2 * q + 1] = dn;
+          } else {
+            v[q] = dp;
+          }
         }
         int nv = NV;
 #pragma unroll
@@ -188,18 +208,18 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
         }
         constexpr int kLanesPerVal = LPR / NV;
         const int j = gl / kLanesPerVal;                 // the score this lane finishes
-        const bool is_neg = j & 1;
+        const bool is_neg = TWO ? (j & 1) : (a.label == 0);
         const float z = is_neg ? v[0] : -v[0];           // loss term = softplus(z)
         const float spv = softplus(z);
-        if ((gl % kLanesPerVal) == 0 && (j >> 1) < bsz) {
+        if ((gl % kLanesPerVal) == 0 && (TWO ? (j >> 1) : j) < bsz) {
           if (is_neg) sn_sum += spv; else sp_sum += spv;
         }
         if (want_grad) {
           const float coef = (is_neg ? 1.f : -wbar) * sigmoid(z) * a.inv_e;
 #pragma unroll
           for (int q = 0; q < kUnroll; ++q) {
-            const float cpos = __shfl_sync(gmask, coef, (2 * q) * kLanesPerVal, LPR);
-            const float cneg = __shfl_sync(gmask, coef, (2 * q + 1) * kLanesPerVal, LPR);
+            const float cpos = __shfl_sync(gmask, coef, (TWO ? 2 * q : q) * kLanesPerVal, LPR);
+            const float cneg = TWO ? __shfl_sync(gmask, coef, (2 * q + 1) * kLanesPerVal, LPR) : 0.f;
             if (q < bsz) {
               if (gl == t + q) {
                 my_cpos = cpos;
@@ -210,10 +230,10 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
                 if (act[i]) {
                   float fp[kVec], fn[kVec];
                   Elem<T>::unpack(vp[q][i], fp);
-                  Elem<T>::unpack(vn[q][i], fn);
+                  if (TWO) Elem<T>::unpack(vn[q][i], fn);
 #pragma unroll
                   for (int k = 0; k < kVec; ++k)
-                    ga[i][k] = fmaf(cpos, fp[k], fmaf(cneg, fn[k], ga[i][k]));
+                    ga[i][k] = TWO ? fmaf(cpos, fp[k], fmaf(cneg, fn[k], ga[i][k])) : fmaf(cpos, fp[k], ga[i][k]);
                 }
             }
           }
@@ -222,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
       }
       if (want_grad && e0 + gl < e_end) {
         a.c_pos[id_cur] = my_cpos;
-        a.c_neg[id_cur] = my_cneg;
+        if (TWO) a.c_neg[id_cur] = my_cneg;
       }
       e0 += LPR;
       cp_cur = cp_nxt; id_cur = id_nxt; cn_cur = cn_nxt;
@@ -287,14 +307,14 @@ __global__ void __launch_bounds__(1024) edge_bce_finish(const double* __restrict
   }
 }
 
-template <typename T>
+template <typename T, bool TWO>
 int launch_bce(BceArgs& a, int64_t* n_blocks_out, cudaStream_t st, bool dry) {
   const int rv = a.row_vecs;
 #define TRG_BCE_CASE(LPR, VPL, R)                                                     \
   {                                                                                   \
     const int64_t grid = ceil_div<int64_t>(a.n_users, (int64_t)(kThreads / LPR) * R); \
     *n_blocks_out = grid;                                                             \
-    if (!dry) edge_bce<T, LPR, VPL, R><<<(unsigned)grid, kThreads, 0, st>>>(a);       \
+    if (!dry) edge_bce<T, LPR, VPL, R, TWO><<<(unsigned)grid, kThreads, 0, st>>>(a);  \
   }
   if (rv <= 2) TRG_BCE_CASE(2, 1, 1)
   else if (rv <= 4) TRG_BCE_CASE(4, 1, 2)
@@ -352,13 +372,58 @@ extern "C" int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, c
   a.row_vecs = hidden * es / 16;
   int64_t n_blocks = 0;
   if (n_users > 0) {
-    int rc = dtype == TRG_F32 ? launch_bce<float>(a, &n_blocks, st, false)
-                              : launch_bce<__nv_bfloat16>(a, &n_blocks, st, false);
+    int rc = dtype == TRG_F32 ? launch_bce<float, true>(a, &n_blocks, st, false)
+                              : launch_bce<__nv_bfloat16, true>(a, &n_blocks, st, false);
     if (rc) return rc;
     count_launch();
     TRG_LAUNCH_OK();
   }
   edge_bce_finish<<<1, 1024, 0, st>>>(a.partials, n_blocks, wbar, (double)n_edges, loss_out);
+  count_launch();
+  TRG_LAUNCH_OK();
+  return TRG_OK;
+}
+
+extern "C" int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                                    const void* anchor, const void* gathered, int64_t n_rows,
+                                    int64_t n_edges_scale, int32_t hidden, int dtype, int label,
+                                    const float* wbar, float* loss_out, float* coef_out, void* g_anchor,
+                                    int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  TRG_CHECK_ARG(n_rows >= 0 && n_edges_scale >= 0, "trg_edge_anchor_loss: negative size");
+  TRG_CHECK_ARG(loss_out && wbar, "trg_edge_anchor_loss: NULL loss_out/wbar");
+  TRG_CHECK_ARG((coef_out == nullptr) == (g_anchor == nullptr),
+                "trg_edge_anchor_loss: coef_out and g_anchor must be both NULL or both non-NULL");
+  TRG_CHECK_ARG(n_rows == 0 || (rowptr && anchor), "trg_edge_anchor_loss: NULL rowptr / anchor table");
+  TRG_CHECK_ARG(((uintptr_t)anchor | (uintptr_t)gathered | (uintptr_t)g_anchor) % 16 == 0,
+                "trg_edge_anchor_loss: tables must be 16-byte aligned");
+  TRG_CHECK_ARG(dtype == TRG_F32 || dtype == TRG_BF16, "trg_edge_anchor_loss: unknown dtype %d", dtype);
+  const int es = dtype == TRG_BF16 ? 2 : 4;
+  TRG_CHECK_ARG(hidden > 0 && (hidden * es) % 16 == 0,
+                "trg_edge_anchor_loss: row width %d x %d bytes is not a multiple of 16 bytes", hidden, es);
+  if (workspace == nullptr || workspace_bytes < trg_edge_bce_workspace_bytes(n_rows)) {
+    set_error("trg_edge_anchor_loss: workspace %zu < required %zu", workspace_bytes,
+              trg_edge_bce_workspace_bytes(n_rows));
+    return TRG_E_WORKSPACE;
+  }
+  BceArgs a{};
+  a.rowptr = rowptr; a.col_p = col; a.eid = eid; a.neg_p = nullptr;
+  a.u = anchor; a.p = gathered; a.wbar = wbar; a.c_pos = coef_out; a.c_neg = nullptr; a.g_u = g_anchor;
+  a.partials = reinterpret_cast<double*>(workspace);
+  a.n_users = n_rows;
+  a.inv_e = n_edges_scale > 0 ? (float)(1.0 / (double)n_edges_scale) : 0.f;
+  a.row_vecs = hidden * es / 16;
+  a.label = label ? 1 : 0;
+  a.accumulate = accumulate ? 1 : 0;
+  int64_t n_blocks = 0;
+  if (n_rows > 0) {
+    int rc = dtype == TRG_F32 ? launch_bce<float, false>(a, &n_blocks, st, false)
+                              : launch_bce<__nv_bfloat16, false>(a, &n_blocks, st, false);
+    if (rc) return rc;
+    count_launch();
+    TRG_LAUNCH_OK();
+  }
+  edge_bce_finish<<<1, 1024, 0, st>>>(a.partials, n_blocks, wbar, (double)n_edges_scale, loss_out);
   count_launch();
   TRG_LAUNCH_OK();
   return TRG_OK;

@@ -74,10 +74,13 @@ class ShardedGraph:
             n_src_pad = n_of[rel[0]][2] * self.world
             self.rels[rel] = RelationGraph(loc, n_src_pad, c)
             self.n_local_edges[rel] = int(loc.size(1))
-        # loss: positives owned by the owner of pos_u (train_gnn.py:259-281)
+        # loss (train_gnn.py:259-281): every term <u, p> is evaluated by the OWNER OF THE POST against
+        # the all-gathered user table (U x H moves instead of the 5x larger post table): positives
+        # with pos_p owned here (static), negatives with neg_p owned here (selected every step)
         pos_u, pos_p = train_edge_index[0], train_edge_index[1]
-        self.pos_mask = (pos_u >= self.u0) & (pos_u < self.u1)
-        self.train_local = torch.stack([pos_u[self.pos_mask] - self.u0, pos_p[self.pos_mask]]).contiguous()
+        self.pos_u_global = pos_u.contiguous()
+        self.pos_mask = (pos_p >= self.p0) & (pos_p < self.p1)
+        self.pos_local = torch.stack([pos_u[self.pos_mask], pos_p[self.pos_mask] - self.p0]).contiguous()
         self.n_pos_global = int(train_edge_index.size(1))
         w = interaction_type_tensor[pos_p[self.pos_mask] + num_users].float()
         wsum = torch.stack([w.sum(), torch.tensor(float(w.numel()), device=w.device)])
@@ -85,6 +88,12 @@ class ShardedGraph:
             dist.all_reduce(wsum)
         self.wbar = (wsum[0] / wsum[1]).reshape(1).float().contiguous()
         self._layer0_src = None
+
+    def local_negatives(self, neg_p_global):
+        """This rank's share of ``neg_p = torch.randint(0, P, (E,))`` (train_gnn.py:272): the pairs
+        (pos_u[e], neg_p[e]) whose negative post is owned here, as (global user, local post)."""
+        m = (neg_p_global >= self.p0) & (neg_p_global < self.p1)
+        return torch.stack([self.pos_u_global[m], neg_p_global[m] - self.p0]).contiguous()
 
     def layer0_sources(self):
         """Input features are static: gather them once (train_gnn.py:211 moves the graph once)."""
@@ -104,28 +113,77 @@ def forward_sharded(model, shard: ShardedGraph, ops=CUDA_OPS):
     return dst
 
 
-class CudaLossOps:
+class AnchoredLinkLossFn(torch.autograd.Function):
+    """Partial link loss of this rank (post-owner partition) and its backward.  ``prims`` supplies the
+    compute primitives (CUDA kernels in the product, oracle ops in the CPU host-logic tests):
+      prims.anchor_loss(csr, post_local, user_full, E, label, wbar, want_grad, g_post) -> (loss, coef, g_post)
+      prims.wsum(csr, coef, post_local, scale, out) -> out
+      prims.csr(other, key, n_key, n_other) -> CSR"""
+
     @staticmethod
-    def link_loss(user_local, post_full, shard: ShardedGraph, neg_local):
-        from .functional import LinkBCEFn, LinkStructure
-        ls = getattr(shard, "_link", None)
-        if ls is None:
-            ls = LinkStructure.__new__(LinkStructure)
-            from .graph import build_csr
-            pu, pp = shard.train_local[0], shard.train_local[1]
-            n_post_pad = shard.cp * shard.world
-            ls.train_edge_index = shard.train_local
-            ls.num_users, ls.num_posts = shard.cu, n_post_pad
-            ls.n_edges = int(pu.numel())
-            ls.by_user = build_csr(pp, pu, shard.cu, n_post_pad)
-            ls.by_post = build_csr(pu, pp, n_post_pad, shard.cu, validate=False)
-            ls.wbar = shard.wbar
-            ls.n_edges_scale = shard.n_pos_global
-            shard._link = ls
-        return LinkBCEFn.apply(user_local, post_full, neg_local, ls)
+    def forward(ctx, user_full, post_local, neg_pairs, shard, prims):
+        want = user_full.requires_grad or post_local.requires_grad
+        st = shard.loss_structures(prims)
+        n_u_pad = shard.cu * shard.world
+        neg_by_post = prims.csr(neg_pairs[0], neg_pairs[1], shard.cp, n_u_pad)
+        lp, c_pos, g_p = prims.anchor_loss(st["pos_by_post"], post_local, user_full, shard.n_pos_global, 1,
+                                           shard.wbar, want, None)
+        ln, c_neg, g_p = prims.anchor_loss(neg_by_post, post_local, user_full, shard.n_pos_global, 0,
+                                           shard.wbar, want, g_p)
+        ctx.shard, ctx.prims, ctx.st, ctx.want = shard, prims, st, want
+        if want:
+            ctx.save_for_backward(post_local, neg_pairs, c_pos, c_neg, g_p)
+        return (lp + ln).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        post_local, neg_pairs, c_pos, c_neg, g_p = ctx.saved_tensors
+        shard, prims, st = ctx.shard, ctx.prims, ctx.st
+        g = g.reshape(1).float().contiguous()
+        g_user = g_post = None
+        if ctx.needs_input_grad[1]:
+            g_post = g_p * g.to(g_p.dtype)
+        if ctx.needs_input_grad[0]:
+            n_u_pad = shard.cu * shard.world
+            # dloss/du for ALL users touched by local edges; AllGatherRows.backward reduce-scatters it
+            g_user = prims.wsum(st["pos_by_user"], c_pos, post_local, g, None)
+            neg_by_user = prims.csr(neg_pairs[1], neg_pairs[0], n_u_pad, shard.cp)
+            g_user = prims.wsum(neg_by_user, c_neg, post_local, g, g_user)
+        return g_user, g_post, None, None, None
 
 
-CUDA_LOSS_OPS = CudaLossOps()
+class CudaLossPrims:
+    @staticmethod
+    def csr(other, key, n_key, n_other):
+        from .graph import build_csr
+        return build_csr(other, key, n_key, n_other, validate=False)
+
+    @staticmethod
+    def anchor_loss(csr, post_local, user_full, n_edges, label, wbar, want, g_post):
+        from .functional import edge_anchor_loss
+        return edge_anchor_loss(csr, post_local, user_full, n_edges, label, wbar, want, g_post)
+
+    @staticmethod
+    def wsum(csr, coef, post_local, scale, out):
+        from .functional import gather_wsum
+        return gather_wsum(csr, coef, post_local, scale=scale, out=out, accumulate=out is not None)
+
+
+CUDA_LOSS_OPS = CudaLossPrims()
+
+
+def _loss_structures(self, prims):
+    st = getattr(self, "_loss_st", None)
+    if st is None:
+        pu, pp = self.pos_local[0], self.pos_local[1]
+        n_u_pad = self.cu * self.world
+        st = {"pos_by_post": prims.csr(pu, pp, self.cp, n_u_pad),
+              "pos_by_user": prims.csr(pp, pu, n_u_pad, self.cp)}
+        self._loss_st = st
+    return st
+
+
+ShardedGraph.loss_structures = _loss_structures
 
 
 def allreduce_grads(params):
@@ -145,18 +203,18 @@ def allreduce_grads(params):
 def train_step_sharded(model, optimizer, shard: ShardedGraph, neg_p_global=None, neg_p_local=None,
                        ops=CUDA_OPS, loss_ops=CUDA_LOSS_OPS, return_tensor=False):
     """The body of ``train()`` (train_gnn.py:242-285) on a destination partition.  Every rank holds
-    the same weights; the returned loss is the global loss (identical on all ranks)."""
+    the same weights; the returned loss is the global loss (identical on all ranks).
+    ``neg_p_global``: the step's ``torch.randint(0, P, (E,))`` (same array on every rank), or
+    ``neg_p_local``: this rank's share already selected with ``shard.local_negatives``."""
     model.train()
     optimizer.zero_grad()
     out = forward_sharded(model, shard, ops)
-    post_full = all_gather_rows(out["post"])
+    user_full = all_gather_rows(out["user"])
     if neg_p_local is None:
         if neg_p_global is None:
-            neg_p_local = torch.randint(0, shard.num_posts, (shard.train_local.size(1),),
-                                        device=out["user"].device)
-        else:
-            neg_p_local = neg_p_global[shard.pos_mask].contiguous()
-    loss_local = loss_ops.link_loss(out["user"], post_full, shard, neg_p_local)
+            neg_p_global = torch.randint(0, shard.num_posts, (shard.n_pos_global,), device=user_full.device)
+        neg_p_local = shard.local_negatives(neg_p_global)
+    loss_local = AnchoredLinkLossFn.apply(user_full, out["post"], neg_p_local, shard, loss_ops)
     loss_local.backward()
     allreduce_grads(list(model.parameters()))
     optimizer.step()

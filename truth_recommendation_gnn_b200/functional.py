@@ -172,6 +172,35 @@ def edge_bce_fwd(ls: LinkStructure, user_emb, post_emb, neg_p, want_grad: bool):
     return loss, c_pos, c_neg, g_u
 
 
+def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, want_grad, g_anchor=None):
+    """One launch of the post-anchored loss (multi-GPU form of K4): rows of ``csr`` index ``anchor``,
+    ``csr.col`` indexes ``gathered``.  Returns ``(partial loss[1], coef[E_local] | None, g_anchor | None)``."""
+    lib = _lib.load()
+    anchor, gathered = anchor.contiguous(), gathered.contiguous()
+    _check_rows(anchor, "edge_anchor_loss")
+    dev = anchor.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    coef = None
+    accumulate = g_anchor is not None
+    if want_grad:
+        coef = torch.empty(csr.n_edges, dtype=torch.float32, device=dev)
+        if g_anchor is None:
+            g_anchor = torch.empty_like(anchor)
+    else:
+        g_anchor = None
+    ws_bytes = int(lib.trg_edge_bce_workspace_bytes(csr.n_rows))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    e = csr.n_edges
+    rb = anchor.size(1) * anchor.element_size()
+    nbytes = e * (rb + 12) + csr.n_rows * (rb * (2 if want_grad else 1) + 4)
+    _lib.call("trg_edge_anchor_loss", nbytes, lib.trg_edge_anchor_loss,
+              _lib.ptr(csr.rowptr), _lib.ptr(csr.col) if e else None, _lib.ptr(csr.eid) if e else None,
+              _lib.ptr(anchor), _lib.ptr(gathered), csr.n_rows, int(n_edges_scale), anchor.size(1),
+              _lib.dtype_code(anchor.dtype), 1 if label else 0, _lib.ptr(wbar), _lib.ptr(loss), _lib.ptr(coef),
+              _lib.ptr(g_anchor), 1 if (accumulate and want_grad) else 0, _lib.ptr(ws), ws_bytes, _lib.stream())
+    return loss, coef, g_anchor
+
+
 class LinkBCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, user_emb, post_emb, neg_p, ls: LinkStructure):
