@@ -48,3 +48,18 @@ b = EE * (H * es + 12) + 4 * (P + 1) + P * H * es
 print(f"wsum by_post: {t:7.3f} ms {b/t/1e6:7.0f} GB/s", flush=True)
 t = timeit(lambda: trg.build_csr(g.train_edge_index[0], neg, P, U, validate=False))
 print(f"neg csr build: {t:7.3f} ms", flush=True)
+# single-row anchored loss launches (user-anchored, posts gathered): pos + neg as two passes
+eid_long = ls.by_user.eid.long()
+def two_pass():
+    col_neg = neg.index_select(0, eid_long).int()
+    csr_neg = trg.CSR(ls.by_user.rowptr, col_neg, ls.by_user.eid, ls.by_user.n_rows, ls.by_user.n_cols)
+    l1, c1, gu = Fn.edge_anchor_loss(ls.by_user, u.detach(), p.detach(), EE, 1, ls.wbar, True, None)
+    l2, c2, gu = Fn.edge_anchor_loss(csr_neg, u.detach(), p.detach(), EE, 0, ls.wbar, True, gu)
+    return l1 + l2
+t = timeit(two_pass)
+print(f"edge loss as two single-row passes (incl. neg col gather): {t:7.3f} ms", flush=True)
+t = timeit(lambda: Fn.edge_anchor_loss(ls.by_user, u.detach(), p.detach(), EE, 1, ls.wbar, True, None))
+b = EE * (H * es + 12) + U * (2 * H * es + 4)
+print(f"  one pass: {t:7.3f} ms {b/t/1e6:7.0f} GB/s", flush=True)
+lf, _, _, _ = Fn.edge_bce_fwd(ls, u.detach(), p.detach(), neg, True)
+print("  loss fused vs two-pass:", float(lf), float(two_pass()))

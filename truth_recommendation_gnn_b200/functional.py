@@ -202,15 +202,30 @@ def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, wan
 
 
 class LinkBCEFn(torch.autograd.Function):
+    """loss of train_gnn.py:259-281.  Forward = two single-row passes over the positives grouped by
+    user (anchor = user row, read once per user): the positive posts, then the sampled negatives
+    (same grouping, column = neg_p[eid]).  Measured faster than the fused two-row kernel
+    (trg_edge_bce_fwd: 12.5 ms vs 10.6 ms at config 2) because each pass keeps 8 row loads in flight
+    with half the per-edge bookkeeping; dL/du is accumulated across the two passes without atomics."""
+
     @staticmethod
     def forward(ctx, user_emb, post_emb, neg_p, ls: LinkStructure):
         want = user_emb.requires_grad or post_emb.requires_grad
-        loss, c_pos, c_neg, g_u = edge_bce_fwd(ls, user_emb, post_emb, neg_p, want)
+        if neg_p.dtype != torch.int64 or neg_p.numel() != ls.n_edges:
+            raise _lib.TrgError("neg_p must be int64 with one entry per positive edge (train_gnn.py:272)")
+        if getattr(ls, "eid_long", None) is None:
+            ls.eid_long = ls.by_user.eid.long()
+        e_scale = int(getattr(ls, "n_edges_scale", ls.n_edges))
+        bu = ls.by_user
+        col_neg = neg_p.index_select(0, ls.eid_long).int()     # negatives in the by-user edge order
+        neg_csr = CSR(bu.rowptr, col_neg, bu.eid, bu.n_rows, bu.n_cols)
+        l_pos, c_pos, g_u = edge_anchor_loss(bu, user_emb, post_emb, e_scale, 1, ls.wbar, want, None)
+        l_neg, c_neg, g_u = edge_anchor_loss(neg_csr, user_emb, post_emb, e_scale, 0, ls.wbar, want, g_u)
         ctx.ls = ls
         ctx.want = want
         if want:
             ctx.save_for_backward(user_emb, neg_p, c_pos, c_neg, g_u)
-        return loss.reshape(())
+        return (l_pos + l_neg).reshape(())
 
     @staticmethod
     def backward(ctx, g):
