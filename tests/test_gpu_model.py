@@ -195,3 +195,26 @@ def test_cold_start_batch_matches_per_user_forward(dev):
         ev, ei = otopk.score_topk(e, cat, 10)
         assert_close(vals[i:i + 1].cpu(), ev, TOL_F32, "cold-start scores")
         assert torch.equal(ids[i:i + 1].cpu(), ei)
+
+
+def test_csr_cache_round_trip_skips_k0(dev, tmp_path):
+    """§8f N3: CSR structures persisted next to the graph artefact; loading installs them without
+    launching the K0 sort, and the model output is unchanged."""
+    from truth_recommendation_gnn_b200 import _lib, graph_io
+    g = synth.synth_graph(300, 800, 5000, 1200, 64, seed=11).to(dev)
+    sd = synth.init_state_dict(64, 64, 2)
+    model = _gpu_model(64, 2, sd, dev)
+    out = model(g.x_dict, g.edge_index_dict)
+    (out["user"].sum() + out["post"].sum()).backward()      # builds the transposed structures too
+    path = str(tmp_path / "csr_cache.pt")
+    graph_io.save_csr_cache(path, g.edge_index_dict, g.x_dict)
+    trg.clear_cache()
+    assert graph_io.load_csr_cache(path, g.edge_index_dict, g.x_dict) == 3
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        out2 = model(g.x_dict, g.edge_index_dict)
+    n1 = _lib.launch_count()
+    with torch.no_grad():
+        model(g.x_dict, g.edge_index_dict)
+    assert n1 - n0 == _lib.launch_count() - n1               # first forward after load == steady state: no K0
+    assert torch.equal(out2["user"], out["user"].detach()) and torch.equal(out2["post"], out["post"].detach())

@@ -96,3 +96,39 @@ def test_synth_is_deterministic_and_in_reference_format():
     assert g1.mp_edges == 2 * 200 + 60
     w = g1.interaction_type_tensor
     assert w.shape == (80,) and set(w[30:].tolist()) <= {1.0, 3.0} and float(w[:30].abs().sum()) == 0.0
+
+
+def test_vectorised_graph_prep_matches_reference_loops():
+    """§8f N4: vectorised edge-list construction / weight table == the iterrows loops
+    (train_gnn.py:40-73, 226-237), including unmapped ids and repeated post ids."""
+    import numpy as np
+    import pandas as pd
+    from oracle import graph_prep as oprep
+    from truth_recommendation_gnn_b200 import graph_io
+    rng = np.random.default_rng(0)
+    users = [f"u{i}" for i in range(40)]
+    n = 500
+    df = pd.DataFrame({
+        "engager": rng.choice(users + ["ghost"], n), "target_user": rng.choice(users + ["nobody"], n),
+        "post_id": rng.integers(0, 120, n), "interaction": rng.choice(["QT", "RE", "POST"], n),
+        "timestamp": rng.integers(0, 10_000, n)})
+    user_to_idx = {u: i for i, u in enumerate(sorted(users))}
+    post_to_idx = {i: len(users) + i for i in range(100)}          # posts 100..119 unmapped
+    e_ref, a_ref = oprep.build_edge_index_safe(df, user_to_idx, post_to_idx)
+    e, a = graph_io.build_edge_index(df, user_to_idx, post_to_idx)
+    assert torch.equal(e, e_ref) and torch.equal(a, a_ref) and e.dtype == torch.int64
+    train = df[df["post_id"] < 100].sort_values("timestamp").reset_index(drop=True)
+    assert torch.equal(graph_io.interaction_type_table(train, post_to_idx), oprep.interaction_type_table(train, post_to_idx))
+
+
+def test_hetero_inputs_follow_train_gnn_assembly():
+    from truth_recommendation_gnn_b200 import graph_io
+    nu, np_ = 5, 7
+    data = {"num_users": nu, "num_posts": np_, "x": torch.arange((nu + np_) * 4.0).reshape(nu + np_, 4),
+            "edge_index_social": torch.tensor([[0, 1, 4], [2, 2, 0]])}
+    train_engage = torch.tensor([[0, 3, 4, 9, 2], [nu + 1, nu + 6, nu + 7, nu + 2, nu - 1]])   # 3 invalid rows
+    x_dict, ei = graph_io.hetero_inputs(data, train_engage)
+    assert x_dict["user"].shape == (nu, 4) and x_dict["post"].shape == (np_, 4)
+    assert ei[trg.REL_ENGAGE].tolist() == [[0, 3], [1, 6]]
+    assert torch.equal(ei[trg.REL_DIRECT], ei[trg.REL_ENGAGE].flip(0))
+    assert torch.equal(ei[trg.REL_SOCIAL], data["edge_index_social"])
