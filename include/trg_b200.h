@@ -55,6 +55,24 @@ int trg_csr_build(const int64_t* other, const int64_t* key, int64_t n_edges, int
                   int32_t* rowptr /* [n_key+1] */, int32_t* col /* [E] */, int32_t* eid /* [E] */,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Long-row splitting for skewed degree distributions (all optional: pass NULL when no row is long).
+ * Rows longer than the caller's threshold T are cut into <= T-edge slices ("virtual rows"); slices
+ * accumulate raw fp32 partial sums which a second small kernel adds up in slice order, so the result
+ * is deterministic (it equals the sequential sum to fp32 rounding, not bit for bit, for those rows).
+ *   vrowptr[n_vrows+1]: edge offsets of the virtual rows (consecutive, covering every edge once);
+ *   vinfo[n_vrows]    : >= 0 = the (short) row this virtual row is; < 0 = partial slot -(v+1);
+ *   long_rows[n_long], long_ptr[n_long+1]: the long rows and their slot ranges;
+ *   partial           : fp32 workspace [n_slots, feat]. */
+typedef struct {
+  const int32_t* vrowptr;
+  const int32_t* vinfo;
+  int64_t n_vrows;
+  const int32_t* long_rows;
+  const int32_t* long_ptr;
+  int64_t n_long;
+  float* partial;
+} trg_long_rows;
+
 /* ---- A1+A2 / K1: fused gather + segmented mean (SAGEConv propagate + MeanAggregation) ------------
  * Replaces x_j = x_src.index_select(0, src); scatter(x_j, dst, reduce='mean') inside the
  * SAGEConv calls at train_gnn.py:177-184,194-197.  mean[r] = (sum_{j in row r} x_src[col[j]]) /
@@ -63,7 +81,7 @@ int trg_csr_build(const int64_t* other, const int64_t* key, int64_t n_edges, int
 int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_src,
                      int64_t n_dst, int32_t feat, int dtype,
                      void* mean_out /* [n_dst, feat] dtype */, float* inv_deg_out /* [n_dst] */,
-                     void* stream);
+                     const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
 
 /* ---- A7 / K2: atomic-free backward of K1 w.r.t. the sources (layers >= 2) ----------------------
  * Replaces autograd of index_select + scatter-mean (index_add / gather).  Uses the transposed
@@ -71,7 +89,8 @@ int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_sr
  *     g_src[s] = sum_{j in row s} g_mean[col_t[j]] * inv_deg[col_t[j]]      (inv_deg nullable) */
 int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
                      const void* g_mean, int64_t n_src, int32_t feat, int dtype,
-                     void* g_src_out /* [n_src, feat] dtype */, void* stream);
+                     void* g_src_out /* [n_src, feat] dtype */,
+                     const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
 
 /* ---- generic weighted segmented gather-sum (used by the loss backward) ------------------------
  *     out[r] (+)= scale * sum_{j in row r} coef[eid[j]] * x[col[j]]
@@ -79,7 +98,7 @@ int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float*
 int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                     const float* coef, const float* scale, const void* x,
                     int64_t n_rows, int32_t feat, int dtype, void* out, int accumulate,
-                    void* stream);
+                    const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
 
 /* ---- A5+A6 / K4: fused positive/negative edge score + BCE-with-logits -------------------------
  * Replaces train_gnn.py:259-281:  pos = <u[pos_u], p[pos_p]>, neg = <u[pos_u], p[neg_p]>,

@@ -98,9 +98,45 @@ def test_agg_fwd_edge_cases(dev):
     torch.set_num_threads(1)
     x, ei = _agg_case(300, 50, 20_000, 64, 3, skew=True)
     ei = torch.cat([ei, ei[:, :500]], dim=1)
-    mean, _ = osage.scatter_mean(x.index_select(0, ei[0]), ei[1], 50)
+    mean, cnt = osage.scatter_mean(x.index_select(0, ei[0]), ei[1], 50)
     out, _ = Fn.sage_agg_fwd(trg.RelationGraph(ei.to(dev), 300, 50).fwd, x.to(dev))
-    assert torch.equal(out.cpu(), mean)
+    from truth_recommendation_gnn_b200.graph import LONG_ROW_THRESHOLD
+    deg = torch.bincount(ei[1], minlength=50)
+    short = deg <= LONG_ROW_THRESHOLD
+    assert short.any() and (~short).any()
+    assert torch.equal(out.cpu()[short], mean[short])            # sequential CSR-order sum: bit-exact
+    assert_close(out.cpu()[~short], mean[~short], TOL_F32, "hub rows (split into slices)")
+
+
+@pytest.mark.parametrize("f,dtype,tol", [(128, torch.float32, TOL_F32), (64, torch.float32, TOL_F32),
+                                         (128, torch.bfloat16, TOL_BF16)])
+def test_long_row_splitting(dev, f, dtype, tol, monkeypatch):
+    """Hub rows (power-law degrees) are cut into slices summed by a second kernel: same values to
+    fp32 rounding, deterministic, forward / backward / weighted sum."""
+    from truth_recommendation_gnn_b200 import graph as G
+    monkeypatch.setattr(G, "LONG_ROW_THRESHOLD", 500)
+    x, ei = _agg_case(3000, 400, 60_000, f, 77, skew=True)          # row 0 collects ~13% of the edges
+    x = x.to(dtype).float()
+    rel = trg.RelationGraph(ei.to(dev), 3000, 400)
+    lr = rel.fwd.long_rows()
+    assert lr is not None and lr.long_rows.numel() >= 3 and lr.n_slots > lr.long_rows.numel()
+    xr = x.clone().requires_grad_(True)
+    mean, cnt = osage.scatter_mean(xr.index_select(0, ei[0]), ei[1], 400)
+    gup = torch.randn(400, f, generator=torch.Generator().manual_seed(2)).to(dtype).float()
+    mean.backward(gup)
+    xd = x.to(dev).to(dtype).requires_grad_(True)
+    out = trg.sage_mean_aggregate(xd, rel)
+    out.backward(gup.to(dev).to(dtype))
+    assert_close(out.float().cpu(), mean.detach(), tol, "split-row mean")
+    assert_close(xd.grad.float().cpu(), xr.grad, tol, "split-row backward (transposed CSR has hub sources)")
+    out2 = trg.sage_mean_aggregate(xd.detach(), rel)
+    assert torch.equal(out2, out.detach())                           # deterministic
+    coef = torch.randn(60_000, generator=torch.Generator().manual_seed(3))
+    exp = torch.zeros(400, f, dtype=torch.float64).index_add_(0, ei[1], coef.double()[:, None] * x.double()[ei[0]])
+    ws = Fn.gather_wsum(rel.fwd, coef.to(dev), x.to(dev).to(dtype))
+    assert_close(ws.float().cpu(), exp, tol, "split-row weighted sum")
+    Fn.gather_wsum(rel.fwd, coef.to(dev), x.to(dev).to(dtype), out=ws, accumulate=True)
+    assert_close(ws.float().cpu(), 2 * exp, 2 * tol, "split-row weighted sum, accumulate")
 
 
 @pytest.mark.parametrize("f", [64, 128, 256])

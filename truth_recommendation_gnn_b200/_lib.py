@@ -22,6 +22,11 @@ class TrgProjTerm(ctypes.Structure):
     _fields_ = [("a", _vp), ("w", _vp), ("k", _i32), ("alpha", ctypes.c_float)]
 
 
+class TrgLongRows(ctypes.Structure):
+    _fields_ = [("vrowptr", _vp), ("vinfo", _vp), ("n_vrows", _i64), ("long_rows", _vp), ("long_ptr", _vp),
+                ("n_long", _i64), ("partial", _vp)]
+
+
 class TrgProjBwdTerm(ctypes.Structure):
     _fields_ = [("w", _vp), ("k", _i32), ("alpha", ctypes.c_float), ("row_scale", _vp), ("d_a", _vp)]
 
@@ -37,9 +42,10 @@ SIGNATURES = {
     "trg_launch_count": (_i64, []),
     "trg_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "trg_csr_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "trg_sage_agg_fwd": (_int, [_vp, _vp, _vp, _i64, _i32, _int, _vp, _vp, _vp]),
-    "trg_sage_agg_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _vp]),
-    "trg_gather_wsum": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int, _vp]),
+    "trg_sage_agg_fwd": (_int, [_vp, _vp, _vp, _i64, _i32, _int, _vp, _vp, ctypes.POINTER(TrgLongRows), _vp]),
+    "trg_sage_agg_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, ctypes.POINTER(TrgLongRows), _vp]),
+    "trg_gather_wsum": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int,
+                               ctypes.POINTER(TrgLongRows), _vp]),
     "trg_edge_bce_workspace_bytes": (_sz, [_i64]),
     "trg_edge_bce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _sz, _vp]),

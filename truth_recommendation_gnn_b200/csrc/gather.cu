@@ -35,6 +35,15 @@ struct GatherArgs {
   int64_t n_rows;
   int row_vecs;  // 16-byte vectors per row
   int accumulate;
+  // long-row splitting (nullable vinfo): rowptr/n_rows then describe VIRTUAL rows; a virtual row is
+  // either a whole short row (vinfo >= 0: its row id) or one <= T-edge slice of a long row
+  // (vinfo < 0: partial-sum slot -(vinfo+1)); slices are summed in order by gather_combine_long
+  const int* vinfo;
+  float* partial;        // [n_slots][feat] fp32
+  const int* long_rows;  // [n_long] original row ids
+  const int* long_ptr;   // [n_long + 1] slot ranges
+  const int* rowptr_orig;
+  int64_t n_long;
 };
 
 template <typename T, int LPR, int VPL, int MODE>
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
 // are prefetched while the current chunk's rows are in flight, and the running sum is flushed at
 // row boundaries.  Removes the per-row rowptr -> col -> row dependency chain that made short rows
 // (in-degree ~8) latency-bound (profiles/README.md, r1_v1).  Same CSR-order adds: still bit-exact.
-template <typename T, int LPR, int VPL, int MODE, int R>
+template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT>
 __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(const GatherArgs a) {
   constexpr int kVec = Elem<T>::kVec;
   constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
@@ -178,10 +187,31 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
   int cur_end = __shfl_sync(gmask, my_ptr, 1, LPR);
 
   auto flush = [&]() {
-    char* ob = reinterpret_cast<char*>(a.out) + (size_t)(r0 + cur) * row_bytes + (size_t)gl * 16;
+    int64_t orow = r0 + cur;
+    if (VIRT) {
+      const int info = __ldg(a.vinfo + r0 + cur);
+      if (info < 0) {   // slice of a long row: raw fp32 partial sum, combined later in slice order
+        float* pb = a.partial + (size_t)(-(info + 1)) * ((size_t)a.row_vecs * kVec);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          if (act[i]) {
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) pb[(size_t)(gl + i * LPR) * kVec + k] = acc[i][k];
+          }
+#pragma unroll
+          for (int k = 0; k < kVec; ++k) acc[i][k] = 0.f;
+        }
+        ++cur;
+        cur_beg = cur_end;
+        cur_end = __shfl_sync(gmask, my_ptr, min(cur + 1, nr), LPR);
+        return;
+      }
+      orow = info;
+    }
+    char* ob = reinterpret_cast<char*>(a.out) + (size_t)orow * row_bytes + (size_t)gl * 16;
     if (MODE == kMean) {
       const float cntf = (float)max(cur_end - cur_beg, 1);
-      if (gl == 0 && a.inv_deg_out) a.inv_deg_out[r0 + cur] = __fdiv_rn(1.f, cntf);
+      if (gl == 0 && a.inv_deg_out) a.inv_deg_out[orow] = __fdiv_rn(1.f, cntf);
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
 #pragma unroll
@@ -279,6 +309,31 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
   while (cur < nr) flush();                                 // last row and trailing empty rows
 }
 
+// Second stage for long rows: sum the slices' fp32 partials in slice order (deterministic), then the
+// mode's epilogue (mean / scale / accumulate).  One CTA per long row.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128) gather_combine_long(const GatherArgs a) {
+  const int i = blockIdx.x;
+  const int64_t orow = a.long_rows[i];
+  const int s0 = a.long_ptr[i], s1 = a.long_ptr[i + 1];
+  const int feat = a.row_vecs * Elem<T>::kVec;
+  const float post = (MODE != kMean && a.scale) ? __ldg(a.scale) : 1.f;
+  const float cntf = (float)max(a.rowptr_orig[orow + 1] - a.rowptr_orig[orow], 1);
+  if (MODE == kMean && threadIdx.x == 0 && a.inv_deg_out) a.inv_deg_out[orow] = __fdiv_rn(1.f, cntf);
+  T* out = reinterpret_cast<T*>(a.out) + (size_t)orow * feat;
+  for (int f = threadIdx.x; f < feat; f += blockDim.x) {
+    float s = 0.f;
+    for (int sl = s0; sl < s1; ++sl) s += a.partial[(size_t)sl * feat + f];
+    if (MODE == kMean) {
+      s = __fdiv_rn(s, cntf);
+    } else {
+      s *= post;
+      if (a.accumulate) s += (float)out[f];
+    }
+    out[f] = (T)s;
+  }
+}
+
 template <typename T, int MODE>
 int launch_gather(const GatherArgs& a, cudaStream_t st) {
   if (a.n_rows == 0) return TRG_OK;
@@ -291,7 +346,10 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
 #define TRG_GATHER_SEG(LPR, VPL, R)                                                       \
   {                                                                                       \
     const int64_t grid = ceil_div<int64_t>(a.n_rows, (int64_t)(kThreads / LPR) * R);      \
-    gather_reduce_seg<T, LPR, VPL, MODE, R><<<(unsigned)grid, kThreads, 0, st>>>(a);      \
+    if (a.vinfo)                                                                          \
+      gather_reduce_seg<T, LPR, VPL, MODE, R, true><<<(unsigned)grid, kThreads, 0, st>>>(a);  \
+    else                                                                                  \
+      gather_reduce_seg<T, LPR, VPL, MODE, R, false><<<(unsigned)grid, kThreads, 0, st>>>(a); \
   }
   if (rv <= 1) TRG_GATHER_CASE(1, 1)
   else if (rv <= 2) TRG_GATHER_CASE(2, 1)
@@ -309,6 +367,11 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
 #undef TRG_GATHER_SEG
   count_launch();
   TRG_LAUNCH_OK();
+  if (a.vinfo && a.n_long > 0) {
+    gather_combine_long<T, MODE><<<(unsigned)a.n_long, 128, 0, st>>>(a);
+    count_launch();
+    TRG_LAUNCH_OK();
+  }
   return TRG_OK;
 }
 
@@ -318,6 +381,22 @@ int dispatch(const GatherArgs& a, int dtype, cudaStream_t st) {
   if (dtype == TRG_BF16) return launch_gather<__nv_bfloat16, MODE>(a, st);
   set_error("gather: unknown dtype %d", dtype);
   return TRG_E_ARG;
+}
+
+int apply_long(GatherArgs& a, const trg_long_rows* lr, const int32_t* rowptr, const char* who) {
+  if (!lr || lr->n_long <= 0) return TRG_OK;
+  if (a.row_vecs < 5) {
+    set_error("%s: long-row splitting needs rows of at least 80 bytes", who);
+    return TRG_E_UNSUPPORTED;
+  }
+  if (!lr->vrowptr || !lr->vinfo || !lr->long_rows || !lr->long_ptr || !lr->partial) {
+    set_error("%s: incomplete trg_long_rows", who);
+    return TRG_E_ARG;
+  }
+  a.rowptr_orig = rowptr;
+  a.rowptr = lr->vrowptr; a.vinfo = lr->vinfo; a.n_rows = lr->n_vrows;
+  a.partial = lr->partial; a.long_rows = lr->long_rows; a.long_ptr = lr->long_ptr; a.n_long = lr->n_long;
+  return TRG_OK;
 }
 
 int row_vecs_of(int feat, int dtype, const char* who, int* out) {
@@ -337,7 +416,7 @@ using namespace trg;
 
 extern "C" int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_src,
                                 int64_t n_dst, int32_t feat, int dtype, void* mean_out,
-                                float* inv_deg_out, void* stream) {
+                                float* inv_deg_out, const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_dst >= 0, "trg_sage_agg_fwd: n_dst < 0");
   if (n_dst == 0) return TRG_OK;
   TRG_CHECK_ARG(rowptr && mean_out, "trg_sage_agg_fwd: NULL rowptr/out");
@@ -347,12 +426,14 @@ extern "C" int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const
   if (rc) return rc;
   a.rowptr = rowptr; a.col = col; a.x = x_src; a.out = mean_out; a.inv_deg_out = inv_deg_out;
   a.n_rows = n_dst;
+  rc = apply_long(a, lr, rowptr, "trg_sage_agg_fwd");
+  if (rc) return rc;
   return dispatch<kMean>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
                                 const void* g_mean, int64_t n_src, int32_t feat, int dtype,
-                                void* g_src_out, void* stream) {
+                                void* g_src_out, const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_src >= 0, "trg_sage_agg_bwd: n_src < 0");
   if (n_src == 0) return TRG_OK;
   TRG_CHECK_ARG(rowptr_t && g_src_out, "trg_sage_agg_bwd: NULL rowptr/out");
@@ -362,12 +443,15 @@ extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, c
   if (rc) return rc;
   a.rowptr = rowptr_t; a.col = col_t; a.nbr_scale = inv_deg; a.x = g_mean; a.out = g_src_out;
   a.n_rows = n_src;
+  rc = apply_long(a, lr, rowptr_t, "trg_sage_agg_bwd");
+  if (rc) return rc;
   return dispatch<kNbrScale>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                                const float* coef, const float* scale, const void* x, int64_t n_rows,
-                               int32_t feat, int dtype, void* out, int accumulate, void* stream) {
+                               int32_t feat, int dtype, void* out, int accumulate,
+                               const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_rows >= 0, "trg_gather_wsum: n_rows < 0");
   if (n_rows == 0) return TRG_OK;
   TRG_CHECK_ARG(rowptr && out, "trg_gather_wsum: NULL rowptr/out");
@@ -377,5 +461,7 @@ extern "C" int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const 
   if (rc) return rc;
   a.rowptr = rowptr; a.col = col; a.eid = eid; a.coef = coef; a.scale = scale; a.x = x; a.out = out;
   a.n_rows = n_rows; a.accumulate = accumulate;
+  rc = apply_long(a, lr, rowptr, "trg_gather_wsum");
+  if (rc) return rc;
   return dispatch<kEdgeCoef>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -13,6 +13,17 @@ from . import _lib
 from .graph import CSR, RelationGraph, build_csr
 
 
+def _long_rows_arg(csr: CSR, feat: int, dev):
+    """ctypes ``trg_long_rows`` (+ the tensors it points to, to keep them alive) or ``(None, None)``."""
+    lr = csr.long_rows() if feat * 4 >= 80 else None
+    if lr is None:
+        return None, None
+    partial = torch.empty(lr.n_slots, feat, dtype=torch.float32, device=dev)
+    s = _lib.TrgLongRows(_lib.ptr(lr.vrowptr), _lib.ptr(lr.vinfo), int(lr.vinfo.numel()), _lib.ptr(lr.long_rows),
+                         _lib.ptr(lr.long_ptr), int(lr.long_rows.numel()), _lib.ptr(partial))
+    return ctypes.byref(s), (s, partial)
+
+
 def _check_rows(x: torch.Tensor, what: str):
     es = x.element_size()
     if x.dim() != 2 or (x.size(1) * es) % 16 != 0:
@@ -33,9 +44,10 @@ def sage_agg_fwd(csr: CSR, x_src: torch.Tensor, want_inv_deg: bool = True):
     if csr.n_rows:
         rb = x_src.size(1) * x_src.element_size()
         nbytes = csr.n_edges * (rb + 4) + 4 * (csr.n_rows + 1) + csr.n_rows * rb
+        lr, keep = _long_rows_arg(csr, x_src.size(1), x_src.device)
         _lib.call("trg_sage_agg_fwd", nbytes, lib.trg_sage_agg_fwd,
                   _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(x_src), csr.n_rows, x_src.size(1),
-                  _lib.dtype_code(x_src.dtype), _lib.ptr(out), _lib.ptr(inv_deg), _lib.stream())
+                  _lib.dtype_code(x_src.dtype), _lib.ptr(out), _lib.ptr(inv_deg), lr, _lib.stream())
     return out, inv_deg
 
 
@@ -49,9 +61,10 @@ def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor):
         rb = g_mean.size(1) * g_mean.element_size()
         nbytes = (csr_t.n_edges * (rb + 4) + 4 * (csr_t.n_rows + 1) + csr_t.n_rows * rb
                   + 4 * csr_t.n_cols)
+        lr, keep = _long_rows_arg(csr_t, g_mean.size(1), g_mean.device)
         _lib.call("trg_sage_agg_bwd", nbytes, lib.trg_sage_agg_bwd,
                   _lib.ptr(csr_t.rowptr), _lib.ptr(csr_t.col), _lib.ptr(inv_deg), _lib.ptr(g_mean),
-                  csr_t.n_rows, g_mean.size(1), _lib.dtype_code(g_mean.dtype), _lib.ptr(out), _lib.stream())
+                  csr_t.n_rows, g_mean.size(1), _lib.dtype_code(g_mean.dtype), _lib.ptr(out), lr, _lib.stream())
     return out
 
 
@@ -96,10 +109,11 @@ def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulat
         rb = x.size(1) * x.element_size()
         nbytes = (csr.n_edges * (rb + 12) + 4 * (csr.n_rows + 1)
                   + csr.n_rows * rb * (2 if accumulate else 1))
+        lr, keep = _long_rows_arg(csr, x.size(1), x.device)
         _lib.call("trg_gather_wsum", nbytes, lib.trg_gather_wsum,
                   _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(csr.eid), _lib.ptr(coef),
                   _lib.ptr(scale), _lib.ptr(x), csr.n_rows, x.size(1), _lib.dtype_code(x.dtype),
-                  _lib.ptr(out), 1 if accumulate else 0, _lib.stream())
+                  _lib.ptr(out), 1 if accumulate else 0, lr, _lib.stream())
     return out
 
 

@@ -15,6 +15,21 @@ import torch
 from . import _lib
 
 
+#: rows with more edges than this are split into slices summed by a second kernel (load balance on
+#: skewed / power-law degree distributions; SURVEY.md §7 hard part 2)
+LONG_ROW_THRESHOLD = 1024
+
+
+@dataclass
+class LongRows:
+    """Virtual-row view of a CSR with long rows cut into <= T-edge slices (trg_long_rows)."""
+    vrowptr: torch.Tensor    # int32 [n_vrows + 1]
+    vinfo: torch.Tensor      # int32 [n_vrows]: row id, or -(slot + 1) for a slice of a long row
+    long_rows: torch.Tensor  # int32 [n_long]
+    long_ptr: torch.Tensor   # int32 [n_long + 1]
+    n_slots: int
+
+
 @dataclass
 class CSR:
     """Rows = keys (destinations for the forward structure). All int32 on the device."""
@@ -23,10 +38,43 @@ class CSR:
     eid: torch.Tensor      # [E]  original edge position (== argsort(key, stable))
     n_rows: int
     n_cols: int
+    _long: object = None   # LongRows | False (no long rows) | None (not computed yet)
 
     @property
     def n_edges(self) -> int:
         return int(self.col.numel())
+
+    def long_rows(self, threshold: int = None):
+        """``LongRows`` when some row exceeds ``threshold`` edges, else ``None``.  Computed once per
+        CSR (one host read of the maximum degree); static graphs only pay this at cache-fill time."""
+        if self._long is None:
+            self._long = _split_long_rows(self, LONG_ROW_THRESHOLD if threshold is None else threshold) or False
+        return self._long or None
+
+
+def _split_long_rows(csr: "CSR", t: int):
+    if csr.n_rows == 0 or csr.n_edges <= t:
+        return None
+    rp = csr.rowptr.long()
+    deg = rp[1:] - rp[:-1]
+    if int(deg.max()) <= t:
+        return None
+    is_long = deg > t
+    counts = torch.where(is_long, (deg + t - 1) // t, torch.ones_like(deg))
+    n_vrows = int(counts.sum())
+    orig = torch.repeat_interleave(torch.arange(csr.n_rows, device=rp.device), counts)
+    vstart = torch.cumsum(counts, 0) - counts                      # first virtual row of each row
+    k = torch.arange(n_vrows, device=rp.device) - vstart[orig]     # slice index inside its row
+    vrowptr = torch.empty(n_vrows + 1, dtype=torch.int32, device=rp.device)
+    vrowptr[:-1] = (rp[:-1][orig] + k * t).int()
+    vrowptr[-1] = csr.n_edges
+    part = is_long[orig]
+    slot = torch.cumsum(part.long(), 0) - 1
+    vinfo = torch.where(part, -(slot + 1), orig).int()
+    long_ids = is_long.nonzero().flatten()
+    lp = torch.zeros(long_ids.numel() + 1, dtype=torch.long, device=rp.device)
+    lp[1:] = torch.cumsum(counts[long_ids], 0)
+    return LongRows(vrowptr, vinfo, long_ids.int(), lp.int(), int(lp[-1]))
 
 
 def build_csr(other: torch.Tensor, key: torch.Tensor, n_key: int, n_other: int,
