@@ -36,6 +36,9 @@ WORKLOADS = {
     # configs[2]: same graph in bf16 (multi-GPU scaling config)
     "cfg3": dict(num_users=1_000_000, num_posts=5_000_000, e_eng=40_000_000, e_soc=10_000_000,
                  hidden=128, layers=2, dtype="bf16"),
+    # load-balance report: config 2 with Zipf-like destinations, dst = floor(N * u^3)
+    "cfg2skew": dict(num_users=1_000_000, num_posts=5_000_000, e_eng=40_000_000, e_soc=10_000_000,
+                     hidden=128, layers=2, dtype="f32", skew=True),
     # configs[0]: the reference's own CPU-runnable scale
     "cfg1": dict(num_users=10_000, num_posts=50_000, e_eng=400_000, e_soc=100_000,
                  hidden=64, layers=2, dtype="f32"),
@@ -131,7 +134,8 @@ def run_cpu_oracle(w, steps, warmup):
     from oracle import sage as osage   # the one place bench.py executes oracle/: the CPU baseline
     from truth_recommendation_gnn_b200 import synth
     s, desc = cpu_sample_workload(w)
-    g = synth.synth_graph(s["num_users"], s["num_posts"], s["e_eng"], s["e_soc"], s["hidden"], seed=0)
+    g = synth.synth_graph(s["num_users"], s["num_posts"], s["e_eng"], s["e_soc"], s["hidden"], seed=0,
+                          skew=w.get("skew", False))
     H, L = s["hidden"], s["layers"]
     model = (osage.WeightedRGCNOracle(H, (H, H)) if L == 1 else osage.StackedWeightedRGCNOracle(H, L, (H, H)))
     model.load_state_dict(synth.init_state_dict(H, H, L))
@@ -181,7 +185,7 @@ def gpu_train_bench(args, w, rank, world, dev):
     dtype = torch.float32 if w["dtype"] == "f32" else torch.bfloat16
     U, P, Ee, Es, H, L = w["num_users"], w["num_posts"], w["e_eng"], w["e_soc"], w["hidden"], w["layers"]
     t_setup0 = time.perf_counter()
-    g = synth.synth_graph(U, P, Ee, Es, H, seed=0, device=dev, dtype=dtype)   # same graph on every rank
+    g = synth.synth_graph(U, P, Ee, Es, H, seed=0, device=dev, dtype=dtype, skew=w.get("skew", False))   # same graph on every rank
     model = trg.WeightedRGCN(H) if L == 1 else trg.StackedWeightedRGCN(H, L)
     model.load_state_dict(synth.init_state_dict(H, H, L))
     model = model.to(dev).to(dtype)
