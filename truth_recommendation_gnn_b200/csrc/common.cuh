@@ -128,4 +128,55 @@ struct Elem<__nv_bfloat16> {
   }
 };
 
+// ---- vector access of VB = 16 or 8 bytes per lane ------------------------------------------------
+// 8-byte lanes let a FULL warp own one 256-byte row (fp32 H=64, bf16 H=128) instead of two half-warps
+// walking two rows with divergent control flow.
+template <typename T, int VB>
+struct Vec;
+template <typename T>
+struct Vec<T, 16> {
+  using Raw = uint4;
+  static constexpr int kVec = Elem<T>::kVec;
+  __device__ static __forceinline__ Raw load(const void* p) { return ldg_row(p); }
+  __device__ static __forceinline__ Raw load_plain(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static __forceinline__ void unpack(Raw v, float* f) { Elem<T>::unpack(v, f); }
+  __device__ static __forceinline__ void store(void* p, const float* f) { stg_stream(p, Elem<T>::pack(f)); }
+};
+__device__ __forceinline__ uint2 ldg_row8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+template <>
+struct Vec<float, 8> {
+  using Raw = uint2;
+  static constexpr int kVec = 2;
+  __device__ static __forceinline__ Raw load(const void* p) { return ldg_row8(p); }
+  __device__ static __forceinline__ Raw load_plain(const void* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ static __forceinline__ void unpack(Raw v, float* f) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+  }
+  __device__ static __forceinline__ void store(void* p, const float* f) {
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(f[0])), "r"(__float_as_uint(f[1])) : "memory");
+  }
+};
+template <>
+struct Vec<__nv_bfloat16, 8> {
+  using Raw = uint2;
+  static constexpr int kVec = 4;
+  __device__ static __forceinline__ Raw load(const void* p) { return ldg_row8(p); }
+  __device__ static __forceinline__ Raw load_plain(const void* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ static __forceinline__ void unpack(Raw v, float* f) {
+    f[0] = __uint_as_float(v.x << 16);
+    f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16);
+    f[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  __device__ static __forceinline__ void store(void* p, const float* f) {
+    const uint32_t a = Elem<__nv_bfloat16>::pack2(f[0], f[1]), b = Elem<__nv_bfloat16>::pack2(f[2], f[3]);
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+  }
+};
+
 }  // namespace trg

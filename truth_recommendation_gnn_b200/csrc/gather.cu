@@ -155,9 +155,10 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
 // are prefetched while the current chunk's rows are in flight, and the running sum is flushed at
 // row boundaries.  Removes the per-row rowptr -> col -> row dependency chain that made short rows
 // (in-degree ~8) latency-bound (profiles/README.md, r1_v1).  Same CSR-order adds: still bit-exact.
-template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT>
+template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT, int VB = 16>
 __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(const GatherArgs a) {
-  constexpr int kVec = Elem<T>::kVec;
+  using V = Vec<T, VB>;
+  constexpr int kVec = V::kVec;
   constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
   static_assert(R < LPR, "row boundaries are held one per lane");
   const int lane = threadIdx.x & 31;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
   const int my_ptr = ldg_stream(a.rowptr + r0 + min(gl, nr));   // lane l: start of row l (l <= nr)
   const int e_end = __shfl_sync(gmask, my_ptr, nr, LPR);
   int e0 = __shfl_sync(gmask, my_ptr, 0, LPR);
-  const size_t row_bytes = (size_t)a.row_vecs * 16;
+  const size_t row_bytes = (size_t)a.row_vecs * VB;
   const char* xb = reinterpret_cast<const char*>(a.x);
   const float post = (MODE != kMean && a.scale) ? __ldg(a.scale) : 1.f;
 
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
       }
       orow = info;
     }
-    char* ob = reinterpret_cast<char*>(a.out) + (size_t)orow * row_bytes + (size_t)gl * 16;
+    char* ob = reinterpret_cast<char*>(a.out) + (size_t)orow * row_bytes + (size_t)gl * VB;
     if (MODE == kMean) {
       const float cntf = (float)max(cur_end - cur_beg, 1);
       if (gl == 0 && a.inv_deg_out) a.inv_deg_out[orow] = __fdiv_rn(1.f, cntf);
@@ -225,12 +226,12 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
           for (int k = 0; k < kVec; ++k) acc[i][k] *= post;
           if (a.accumulate) {
             float f[kVec];
-            Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)i * LPR * 16), f);
+            V::unpack(V::load_plain(ob + (size_t)i * LPR * VB), f);
 #pragma unroll
             for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
           }
         }
-        stg_stream(ob + (size_t)i * LPR * 16, Elem<T>::pack(acc[i]));
+        V::store(ob + (size_t)i * LPR * VB, acc[i]);
       }
 #pragma unroll
       for (int k = 0; k < kVec; ++k) acc[i][k] = 0.f;
@@ -267,17 +268,17 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
     load_idx(e0 + 2 * LPR + gl, c_nn, aux_nn);
 
     for (int t = 0; t < cnt; t += kUnroll) {
-      uint4 v[kUnroll][VPL];
+      typename V::Raw v[kUnroll][VPL];
       float wv[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int cu = __shfl_sync(gmask, c_cur, t + u, LPR);
         if (MODE != kMean) wv[u] = __shfl_sync(gmask, w_cur, t + u, LPR);
         if (t + u < cnt) {
-          const char* rp = xb + (size_t)cu * row_bytes + (size_t)gl * 16;
+          const char* rp = xb + (size_t)cu * row_bytes + (size_t)gl * VB;
 #pragma unroll
           for (int i = 0; i < VPL; ++i)
-            if (act[i]) v[u][i] = ldg_row(rp + (size_t)i * LPR * 16);
+            if (act[i]) v[u][i] = V::load(rp + (size_t)i * LPR * VB);
         }
       }
 #pragma unroll
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
           for (int i = 0; i < VPL; ++i) {
             if (act[i]) {
               float f[kVec];
-              Elem<T>::unpack(v[u][i], f);
+              V::unpack(v[u][i], f);
 #pragma unroll
               for (int k = 0; k < kVec; ++k) {
                 if (MODE == kMean)
@@ -351,10 +352,21 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
     else                                                                                  \
       gather_reduce_seg<T, LPR, VPL, MODE, R, false><<<(unsigned)grid, kThreads, 0, st>>>(a); \
   }
+#define TRG_GATHER_SEG8()                                                                 \
+  {                                                                                       \
+    GatherArgs b = a;                                                                     \
+    b.row_vecs = a.row_vecs * 2;                                                          \
+    const int64_t grid = ceil_div<int64_t>(b.n_rows, (int64_t)(kThreads / 32) * 8);       \
+    if (b.vinfo)                                                                          \
+      gather_reduce_seg<T, 32, 1, MODE, 8, true, 8><<<(unsigned)grid, kThreads, 0, st>>>(b);  \
+    else                                                                                  \
+      gather_reduce_seg<T, 32, 1, MODE, 8, false, 8><<<(unsigned)grid, kThreads, 0, st>>>(b); \
+  }
   if (rv <= 1) TRG_GATHER_CASE(1, 1)
   else if (rv <= 2) TRG_GATHER_CASE(2, 1)
   else if (rv <= 4) TRG_GATHER_CASE(4, 1)
   else if (rv <= 8) TRG_GATHER_SEG(8, 1, 4)
+  else if (rv == 16) TRG_GATHER_SEG8()          // 256-byte rows: one full warp per row, 8-byte lanes
   else if (rv <= 16) TRG_GATHER_SEG(16, 1, 8)
   else if (rv <= 32) TRG_GATHER_SEG(32, 1, 8)
   else if (rv <= 64) TRG_GATHER_SEG(32, 2, 8)
@@ -365,6 +377,7 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
   }
 #undef TRG_GATHER_CASE
 #undef TRG_GATHER_SEG
+#undef TRG_GATHER_SEG8
   count_launch();
   TRG_LAUNCH_OK();
   if (a.vinfo && a.n_long > 0) {
