@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TRG_ABI_VERSION 1
+#define TRG_ABI_VERSION 2
 
 enum { TRG_F32 = 0, TRG_BF16 = 1 };
 enum {
@@ -86,19 +86,24 @@ int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_sr
 /* ---- A7 / K2: atomic-free backward of K1 w.r.t. the sources (layers >= 2) ----------------------
  * Replaces autograd of index_select + scatter-mean (index_add / gather).  Uses the transposed
  * CSR (rows = sources, col_t = destination of each edge):
- *     g_src[s] = sum_{j in row s} g_mean[col_t[j]] * inv_deg[col_t[j]]      (inv_deg nullable) */
+ *     g_src[s] (+)= sum_{j in row s} g_mean[col_t[j]] * inv_deg[col_t[j]]   (inv_deg nullable)
+ * accumulate != 0 adds to the rows already in g_src_out (autograd's gradient accumulation of a table
+ * that feeds several relations, fused); relu_of (nullable, [n_src, feat] dtype) is the forward
+ * activation the gradient belongs to: rows are finally gated by relu_of > 0, i.e. the ReLU backward
+ * of train_gnn.py:187-198 (aten threshold_backward) fused into the last accumulating pass. */
 int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
                      const void* g_mean, int64_t n_src, int32_t feat, int dtype,
-                     void* g_src_out /* [n_src, feat] dtype */,
+                     void* g_src_out /* [n_src, feat] dtype */, int accumulate, const void* relu_of,
                      const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
 
 /* ---- generic weighted segmented gather-sum (used by the loss backward) ------------------------
  *     out[r] (+)= scale * sum_{j in row r} coef[eid[j]] * x[col[j]]
- * scale is a device scalar (nullable = 1); accumulate != 0 adds to out. */
+ * scale is a device scalar (nullable = 1); accumulate != 0 adds to out; relu_of as in
+ * trg_sage_agg_bwd (applied after the accumulation). */
 int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                     const float* coef, const float* scale, const void* x,
                     int64_t n_rows, int32_t feat, int dtype, void* out, int accumulate,
-                    const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
+                    const void* relu_of, const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
 
 /* ---- A5+A6 / K4: fused positive/negative edge score + BCE-with-logits -------------------------
  * Replaces train_gnn.py:259-281:  pos = <u[pos_u], p[pos_p]>, neg = <u[pos_u], p[neg_p]>,
@@ -125,12 +130,15 @@ int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, const int32_
  * post table), one label per launch: label 1 = positive edges (loss += wbar * sum softplus(-x) / E),
  * label 0 = sampled negatives (loss += sum softplus(x) / E); E = n_edges_scale, the global positive
  * count.  loss_out[0] receives this launch's partial loss; coef_out[eid] = dloss/dx per edge;
- * g_anchor (+)= sum_e coef_e * gathered[col_e] (accumulate != 0 adds to the rows already there). */
+ * g_anchor (+)= sum_e coef_e * gathered[col_e] (accumulate != 0 adds to the rows already there);
+ * relu_gate != 0 finally zeroes g_anchor where the anchor row itself is <= 0 (the anchor table is the
+ * output of the last layer's ReLU, so this is that ReLU's backward, at no extra traffic). */
 int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                          const void* anchor, const void* gathered, int64_t n_rows,
                          int64_t n_edges_scale, int32_t hidden, int dtype, int label,
                          const float* wbar, float* loss_out, float* coef_out, void* g_anchor,
-                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+                         int accumulate, int relu_gate, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- A3+A4 / K3: SAGE projections + relation combine + ReLU ---------------------------------
  * Replaces lin_l(mean) + lin_r(x_dst) of every SAGEConv and the combine of

@@ -191,6 +191,39 @@ def test_gather_wsum(dev):
     assert_close(out.cpu(), 1.5 * exp, TOL_F32, "wsum accumulate")
 
 
+@pytest.mark.parametrize("f,dtype,tol,long_rows", [(128, torch.float32, TOL_F32, False), (64, torch.float32, TOL_F32, False),
+                                                   (16, torch.float32, TOL_F32, False), (8, torch.float32, TOL_F32, False),
+                                                   (128, torch.float32, TOL_F32, True), (128, torch.bfloat16, TOL_BF16, False)])
+def test_gather_epilogue_accumulate_and_relu_gate(dev, f, dtype, tol, long_rows, monkeypatch):
+    """accumulate + relu_of epilogues of K2 / wsum (the fused ReLU backward and gradient
+    accumulation of fused_step): out = where(act > 0, base + gather_sum, 0)."""
+    if long_rows:
+        from truth_recommendation_gnn_b200 import graph as G
+        monkeypatch.setattr(G, "LONG_ROW_THRESHOLD", 64)
+    x, ei = _agg_case(300, 200, 6000, f, 77 + f, skew=True)
+    gen = torch.Generator().manual_seed(9)
+    x = x.to(dtype).float()
+    base = torch.randn(200, f, generator=gen).to(dtype).float()
+    act = torch.relu(torch.randn(200, f, generator=gen)).to(dtype).float()
+    coef = torch.randn(6000, generator=gen)
+    csr = trg.RelationGraph(ei.to(dev), 300, 200).fwd
+    s_plain = torch.zeros(200, f, dtype=torch.float64).index_add_(0, ei[1], x.double()[ei[0]])
+    s_coef = torch.zeros(200, f, dtype=torch.float64).index_add_(0, ei[1], coef.double()[:, None] * x.double()[ei[0]])
+    xd, actd = x.to(dev).to(dtype), act.to(dev).to(dtype)
+    for what, run, ssum in (
+            ("agg_bwd", lambda o, **kw: Fn.sage_agg_bwd(csr, None, xd, out=o, **kw), s_plain),
+            ("wsum", lambda o, **kw: Fn.gather_wsum(csr, coef.to(dev), xd, out=o, **kw), s_coef)):
+        out = run(base.to(dev).to(dtype).clone(), accumulate=True)
+        assert_close(out.float().cpu(), base.double() + ssum, tol, what + " accumulate")
+        out = run(base.to(dev).to(dtype).clone(), accumulate=True, relu_of=actd)
+        exp = torch.where(act > 0, base.double() + ssum, torch.zeros((), dtype=torch.float64))
+        assert_close(out.float().cpu(), exp, tol, what + " accumulate + gate")
+        assert bool((out.float().cpu()[act <= 0] == 0).all())
+        out = run(None, relu_of=actd)
+        exp = torch.where(act > 0, ssum, torch.zeros((), dtype=torch.float64))
+        assert_close(out.float().cpu(), exp, tol, what + " gate only")
+
+
 # ---------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("h,dtype,tol", [(64, torch.float32, TOL_F32), (128, torch.float32, TOL_F32),
                                          (16, torch.float32, TOL_F32), (256, torch.float32, TOL_F32),

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/trg_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "python binding and header disagree"
-    assert _lib.load().trg_abi_version() == 1
+    assert _lib.load().trg_abi_version() == 2
     assert _lib.load().trg_csr_workspace_bytes(1000, 100) > 4 * 4 * 1000
 
 

@@ -43,14 +43,15 @@ SIGNATURES = {
     "trg_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "trg_csr_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "trg_sage_agg_fwd": (_int, [_vp, _vp, _vp, _i64, _i32, _int, _vp, _vp, ctypes.POINTER(TrgLongRows), _vp]),
-    "trg_sage_agg_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, ctypes.POINTER(TrgLongRows), _vp]),
-    "trg_gather_wsum": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int,
+    "trg_sage_agg_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int, _vp,
+                                ctypes.POINTER(TrgLongRows), _vp]),
+    "trg_gather_wsum": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int, _vp,
                                ctypes.POINTER(TrgLongRows), _vp]),
     "trg_edge_bce_workspace_bytes": (_sz, [_i64]),
     "trg_edge_bce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _sz, _vp]),
     "trg_edge_anchor_loss": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _int, _vp, _vp, _vp,
-                                    _vp, _int, _vp, _sz, _vp]),
+                                    _vp, _int, _int, _vp, _sz, _vp]),
     "trg_sage_proj_workspace_bytes": (_sz, [_i32, _i32, _int]),
     "trg_sage_proj_fwd": (_int, [ctypes.POINTER(TrgProjTerm), _i32, _vp, _i64, _i32, _int, _int, _vp,
                                  _vp, _sz, _vp]),
@@ -83,7 +84,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.trg_abi_version() != 1:
+        if lib.trg_abi_version() != 2:
             raise TrgError("libtrg_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

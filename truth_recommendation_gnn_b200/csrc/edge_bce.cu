@@ -30,6 +30,8 @@ struct BceArgs {
   int row_vecs;
   int label;        // single-row mode: 1 = positives (softplus(-x), weight wbar), 0 = negatives
   int accumulate;   // single-row mode: add to the existing anchor-gradient rows
+  int relu_gate;    // single-row mode: zero the anchor gradient where the anchor row is <= 0 (the anchor
+                    // table is a ReLU output: this is the ReLU derivative, fused into the final write)
 };
 
 __device__ __forceinline__ float softplus(float x) {  // log(1 + e^x), stable
@@ -101,6 +103,10 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
               Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)(gl + i * LPR) * 16), f);
 #pragma unroll
               for (int k = 0; k < kVec; ++k) ga[i][k] += f[k];
+            }
+            if (!TWO && a.relu_gate) {
+#pragma unroll
+              for (int k = 0; k < kVec; ++k) ga[i][k] = uf[i][k] > 0.f ? ga[i][k] : 0.f;
             }
             stg_stream(ob + (size_t)(gl + i * LPR) * 16, Elem<T>::pack(ga[i]));
           }
@@ -388,7 +394,8 @@ extern "C" int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, c
                                     const void* anchor, const void* gathered, int64_t n_rows,
                                     int64_t n_edges_scale, int32_t hidden, int dtype, int label,
                                     const float* wbar, float* loss_out, float* coef_out, void* g_anchor,
-                                    int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+                                    int accumulate, int relu_gate, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   TRG_CHECK_ARG(n_rows >= 0 && n_edges_scale >= 0, "trg_edge_anchor_loss: negative size");
   TRG_CHECK_ARG(loss_out && wbar, "trg_edge_anchor_loss: NULL loss_out/wbar");
@@ -415,6 +422,7 @@ extern "C" int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, c
   a.row_vecs = hidden * es / 16;
   a.label = label ? 1 : 0;
   a.accumulate = accumulate ? 1 : 0;
+  a.relu_gate = relu_gate ? 1 : 0;
   int64_t n_blocks = 0;
   if (n_rows > 0) {
     int rc = dtype == TRG_F32 ? launch_bce<float, false>(a, &n_blocks, st, false)

@@ -35,6 +35,7 @@ struct GatherArgs {
   int64_t n_rows;
   int row_vecs;  // 16-byte vectors per row
   int accumulate;
+  const void* relu_of;  // nullable, non-mean modes: [n_rows, feat] forward activation; out = relu_of > 0 ? out : 0
   // long-row splitting (nullable vinfo): rowptr/n_rows then describe VIRTUAL rows; a virtual row is
   // either a whole short row (vinfo >= 0: its row id) or one <= T-edge slice of a long row
   // (vinfo < 0: partial-sum slot -(vinfo+1)); slices are summed in order by gather_combine_long
@@ -145,6 +146,13 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
 #pragma unroll
         for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
       }
+      if (a.relu_of) {
+        float f[kVec];
+        Elem<T>::unpack(ldg_row(reinterpret_cast<const char*>(a.relu_of) + (size_t)row * row_bytes +
+                                (size_t)(gl + i * LPR) * 16), f);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) acc[i][k] = f[k] > 0.f ? acc[i][k] : 0.f;
+      }
     }
     stg_stream(ob + (size_t)i * LPR * 16, Elem<T>::pack(acc[i]));
   }
@@ -229,6 +237,13 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
             V::unpack(V::load_plain(ob + (size_t)i * LPR * VB), f);
 #pragma unroll
             for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
+          }
+          if (a.relu_of) {   // ReLU derivative of the layer that produced the rows this gradient is for
+            float f[kVec];
+            V::unpack(V::load(reinterpret_cast<const char*>(a.relu_of) + (size_t)orow * row_bytes +
+                              (size_t)(gl + i * LPR) * VB), f);
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) acc[i][k] = f[k] > 0.f ? acc[i][k] : 0.f;
           }
         }
         V::store(ob + (size_t)i * LPR * VB, acc[i]);
@@ -330,6 +345,7 @@ __global__ void __launch_bounds__(128) gather_combine_long(const GatherArgs a) {
     } else {
       s *= post;
       if (a.accumulate) s += (float)out[f];
+      if (a.relu_of && !((float)reinterpret_cast<const T*>(a.relu_of)[(size_t)orow * feat + f] > 0.f)) s = 0.f;
     }
     out[f] = (T)s;
   }
@@ -446,16 +462,18 @@ extern "C" int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const
 
 extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
                                 const void* g_mean, int64_t n_src, int32_t feat, int dtype,
-                                void* g_src_out, const trg_long_rows* lr, void* stream) {
+                                void* g_src_out, int accumulate, const void* relu_of,
+                                const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_src >= 0, "trg_sage_agg_bwd: n_src < 0");
   if (n_src == 0) return TRG_OK;
   TRG_CHECK_ARG(rowptr_t && g_src_out, "trg_sage_agg_bwd: NULL rowptr/out");
-  TRG_CHECK_ARG(((uintptr_t)g_mean | (uintptr_t)g_src_out) % 16 == 0, "trg_sage_agg_bwd: tables must be 16-byte aligned");
+  TRG_CHECK_ARG(((uintptr_t)g_mean | (uintptr_t)g_src_out | (uintptr_t)relu_of) % 16 == 0,
+                "trg_sage_agg_bwd: tables must be 16-byte aligned");
   GatherArgs a{};
   int rc = row_vecs_of(feat, dtype, "trg_sage_agg_bwd", &a.row_vecs);
   if (rc) return rc;
   a.rowptr = rowptr_t; a.col = col_t; a.nbr_scale = inv_deg; a.x = g_mean; a.out = g_src_out;
-  a.n_rows = n_src;
+  a.n_rows = n_src; a.accumulate = accumulate; a.relu_of = relu_of;
   rc = apply_long(a, lr, rowptr_t, "trg_sage_agg_bwd");
   if (rc) return rc;
   return dispatch<kNbrScale>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
@@ -463,17 +481,18 @@ extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, c
 
 extern "C" int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                                const float* coef, const float* scale, const void* x, int64_t n_rows,
-                               int32_t feat, int dtype, void* out, int accumulate,
+                               int32_t feat, int dtype, void* out, int accumulate, const void* relu_of,
                                const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_rows >= 0, "trg_gather_wsum: n_rows < 0");
   if (n_rows == 0) return TRG_OK;
   TRG_CHECK_ARG(rowptr && out, "trg_gather_wsum: NULL rowptr/out");
-  TRG_CHECK_ARG(((uintptr_t)x | (uintptr_t)out) % 16 == 0, "trg_gather_wsum: tables must be 16-byte aligned");
+  TRG_CHECK_ARG(((uintptr_t)x | (uintptr_t)out | (uintptr_t)relu_of) % 16 == 0,
+                "trg_gather_wsum: tables must be 16-byte aligned");
   GatherArgs a{};
   int rc = row_vecs_of(feat, dtype, "trg_gather_wsum", &a.row_vecs);
   if (rc) return rc;
   a.rowptr = rowptr; a.col = col; a.eid = eid; a.coef = coef; a.scale = scale; a.x = x; a.out = out;
-  a.n_rows = n_rows; a.accumulate = accumulate;
+  a.n_rows = n_rows; a.accumulate = accumulate; a.relu_of = relu_of;
   rc = apply_long(a, lr, rowptr, "trg_gather_wsum");
   if (rc) return rc;
   return dispatch<kEdgeCoef>(a, dtype, reinterpret_cast<cudaStream_t>(stream));

@@ -51,20 +51,34 @@ def sage_agg_fwd(csr: CSR, x_src: torch.Tensor, want_inv_deg: bool = True):
     return out, inv_deg
 
 
-def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor):
-    """Atomic-free gradient w.r.t. the source table through the transposed CSR."""
+def _check_epilogue(out, relu_of, n_rows, x, who):
+    for t, what in ((out, "out"), (relu_of, "relu_of")):
+        if t is not None and (t.shape != (n_rows, x.size(1)) or t.dtype != x.dtype or not t.is_contiguous()
+                              or t.device != x.device):
+            raise _lib.TrgError(f"{who}: {what} must be a contiguous [{n_rows}, {x.size(1)}] {x.dtype} tensor")
+
+
+def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor, out=None, accumulate=False, relu_of=None):
+    """Atomic-free gradient w.r.t. the source table through the transposed CSR.  ``out`` +
+    ``accumulate`` add to gradient rows already computed (a table feeding several relations);
+    ``relu_of`` gates the final rows by ``relu_of > 0`` (the producing layer's ReLU backward)."""
     lib = _lib.load()
     g_mean = g_mean.contiguous()
     _check_rows(g_mean, "sage_agg_bwd")
-    out = torch.empty(csr_t.n_rows, g_mean.size(1), dtype=g_mean.dtype, device=g_mean.device)
+    _check_epilogue(out, relu_of, csr_t.n_rows, g_mean, "sage_agg_bwd")
+    if out is None:
+        out = torch.empty(csr_t.n_rows, g_mean.size(1), dtype=g_mean.dtype, device=g_mean.device)
+        accumulate = False
     if csr_t.n_rows:
         rb = g_mean.size(1) * g_mean.element_size()
-        nbytes = (csr_t.n_edges * (rb + 4) + 4 * (csr_t.n_rows + 1) + csr_t.n_rows * rb
-                  + 4 * csr_t.n_cols)
+        nbytes = (csr_t.n_edges * (rb + 4) + 4 * (csr_t.n_rows + 1)
+                  + csr_t.n_rows * rb * (1 + bool(accumulate) + (relu_of is not None))
+                  + (4 * csr_t.n_cols if inv_deg is not None else 0))
         lr, keep = _long_rows_arg(csr_t, g_mean.size(1), g_mean.device)
         _lib.call("trg_sage_agg_bwd", nbytes, lib.trg_sage_agg_bwd,
                   _lib.ptr(csr_t.rowptr), _lib.ptr(csr_t.col), _lib.ptr(inv_deg), _lib.ptr(g_mean),
-                  csr_t.n_rows, g_mean.size(1), _lib.dtype_code(g_mean.dtype), _lib.ptr(out), lr, _lib.stream())
+                  csr_t.n_rows, g_mean.size(1), _lib.dtype_code(g_mean.dtype), _lib.ptr(out),
+                  1 if accumulate else 0, _lib.ptr(relu_of), lr, _lib.stream())
     return out
 
 
@@ -98,22 +112,23 @@ def sage_mean_aggregate(x_src: torch.Tensor, rel: RelationGraph, grad_prescaled:
 # ------------------------------------------------------------------------------------------
 # generic weighted gather-sum
 # ------------------------------------------------------------------------------------------
-def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulate=False):
+def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulate=False, relu_of=None):
     lib = _lib.load()
     x = x.contiguous()
     _check_rows(x, "gather_wsum")
+    _check_epilogue(out, relu_of, csr.n_rows, x, "gather_wsum")
     if out is None:
         out = torch.empty(csr.n_rows, x.size(1), dtype=x.dtype, device=x.device)
         accumulate = False
     if csr.n_rows:
         rb = x.size(1) * x.element_size()
         nbytes = (csr.n_edges * (rb + 12) + 4 * (csr.n_rows + 1)
-                  + csr.n_rows * rb * (2 if accumulate else 1))
+                  + csr.n_rows * rb * (1 + bool(accumulate) + (relu_of is not None)))
         lr, keep = _long_rows_arg(csr, x.size(1), x.device)
         _lib.call("trg_gather_wsum", nbytes, lib.trg_gather_wsum,
                   _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(csr.eid), _lib.ptr(coef),
                   _lib.ptr(scale), _lib.ptr(x), csr.n_rows, x.size(1), _lib.dtype_code(x.dtype),
-                  _lib.ptr(out), 1 if accumulate else 0, lr, _lib.stream())
+                  _lib.ptr(out), 1 if accumulate else 0, _lib.ptr(relu_of), lr, _lib.stream())
     return out
 
 
@@ -186,9 +201,11 @@ def edge_bce_fwd(ls: LinkStructure, user_emb, post_emb, neg_p, want_grad: bool):
     return loss, c_pos, c_neg, g_u
 
 
-def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, want_grad, g_anchor=None):
-    """One launch of the post-anchored loss (multi-GPU form of K4): rows of ``csr`` index ``anchor``,
-    ``csr.col`` indexes ``gathered``.  Returns ``(partial loss[1], coef[E_local] | None, g_anchor | None)``."""
+def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, want_grad, g_anchor=None,
+                     relu_gate=False):
+    """One launch of the single-row anchored loss: rows of ``csr`` index ``anchor``, ``csr.col`` indexes
+    ``gathered``.  Returns ``(partial loss[1], coef[E_local] | None, g_anchor | None)``.  ``relu_gate``:
+    the written anchor gradient is zeroed where ``anchor <= 0`` (fused ReLU backward)."""
     lib = _lib.load()
     anchor, gathered = anchor.contiguous(), gathered.contiguous()
     _check_rows(anchor, "edge_anchor_loss")
@@ -211,7 +228,8 @@ def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, wan
               _lib.ptr(csr.rowptr), _lib.ptr(csr.col) if e else None, _lib.ptr(csr.eid) if e else None,
               _lib.ptr(anchor), _lib.ptr(gathered), csr.n_rows, int(n_edges_scale), anchor.size(1),
               _lib.dtype_code(anchor.dtype), 1 if label else 0, _lib.ptr(wbar), _lib.ptr(loss), _lib.ptr(coef),
-              _lib.ptr(g_anchor), 1 if (accumulate and want_grad) else 0, _lib.ptr(ws), ws_bytes, _lib.stream())
+              _lib.ptr(g_anchor), 1 if (accumulate and want_grad) else 0,
+              1 if (relu_gate and want_grad) else 0, _lib.ptr(ws), ws_bytes, _lib.stream())
     return loss, coef, g_anchor
 
 

@@ -8,22 +8,35 @@ from __future__ import annotations
 
 import torch
 
+from . import fused_step
 from .functional import link_bce_loss, score_topk
 
 
 def train_step(model, optimizer, x_dict, edge_index_dict, train_edge_index, interaction_type_tensor,
-               num_users, num_posts, neg_p=None, return_tensor=False):
+               num_users, num_posts, neg_p=None, return_tensor=False, fused=None):
     """One full-batch step.  ``neg_p`` defaults to ``torch.randint(0, num_posts, (E,), device)`` as
     at train_gnn.py:272.  Returns ``loss.item()`` (train_gnn.py:285) or the 0-d device tensor when
-    ``return_tensor`` (no host sync)."""
+    ``return_tensor`` (no host sync).
+
+    ``fused``: ``None`` = take the tape-free forward+loss+backward (``fused_step.loss_and_grads``)
+    whenever the model qualifies, ``False`` = always build the autograd tape and call
+    ``loss.backward()`` (same kernels plus torch's element-wise ReLU-backward / accumulation passes),
+    ``True`` = require the fused path."""
     model.train()
     optimizer.zero_grad()
-    out = model(x_dict, edge_index_dict)
-    user_emb, post_emb = out["user"], out["post"]
-    if neg_p is None:
-        neg_p = torch.randint(0, num_posts, (train_edge_index.size(1),), device=user_emb.device)
-    loss = link_bce_loss(user_emb, post_emb, train_edge_index, neg_p, interaction_type_tensor, num_users)
-    loss.backward()
+    use_fused = fused_step.eligible(model, x_dict) if fused is None else bool(fused)
+    if use_fused:
+        if neg_p is None:
+            neg_p = torch.randint(0, num_posts, (train_edge_index.size(1),), device=x_dict["user"].device)
+        loss = fused_step.loss_and_grads(model, x_dict, edge_index_dict, train_edge_index,
+                                         interaction_type_tensor, num_users, neg_p)
+    else:
+        out = model(x_dict, edge_index_dict)
+        user_emb, post_emb = out["user"], out["post"]
+        if neg_p is None:
+            neg_p = torch.randint(0, num_posts, (train_edge_index.size(1),), device=user_emb.device)
+        loss = link_bce_loss(user_emb, post_emb, train_edge_index, neg_p, interaction_type_tensor, num_users)
+        loss.backward()
     optimizer.step()
     return loss.detach() if return_tensor else loss.item()
 
