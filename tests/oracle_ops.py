@@ -72,3 +72,53 @@ def merge(vals, ids, n_lists, k):
     k_in = vals.size(1) // n_lists
     return otopk.merge_topk([vals[:, i * k_in:(i + 1) * k_in] for i in range(n_lists)],
                             [ids[:, i * k_in:(i + 1) * k_in] for i in range(n_lists)], k)
+
+
+class OracleStepPrims:
+    """Oracle primitives for dist_fused.loss_and_grads_sharded (the names of CudaStepPrims)."""
+
+    @staticmethod
+    def agg_mean(rel, x_src):
+        ei = rel.edge_index
+        mean, cnt = osage.scatter_mean(x_src.index_select(0, ei[0]), ei[1], rel.n_dst)
+        if rel.inv_deg is None:
+            rel.inv_deg = 1.0 / torch.bincount(ei[1], minlength=rel.n_dst).clamp(min=1).float()
+        return mean
+
+    @staticmethod
+    def gather_sum(rel, which, x, out=None, accumulate=False, relu_of=None):
+        g = OracleOps.gather_sum(rel, which, x)
+        if out is not None and accumulate:
+            g = out + g
+        if relu_of is not None:
+            g = torch.where(relu_of > 0, g, torch.zeros_like(g))
+        return g
+
+    @staticmethod
+    def proj_fwd(terms, bias, relu):
+        return OracleOps.project(terms, bias, relu, None)
+
+    @staticmethod
+    def proj_bwd_weight(dz, terms, want_bias):
+        return [alpha * (dz.t() @ a) for a, alpha in terms], (dz.sum(0) if want_bias else None)
+
+    @staticmethod
+    def proj_bwd_input(dz, terms):
+        outs = []
+        for w, alpha, rs in terms:
+            d = alpha * (dz @ w)
+            outs.append(d * rs[:, None] if rs is not None else d)
+        return outs
+
+    csr = staticmethod(OracleLossOps.csr)
+
+    @staticmethod
+    def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate):
+        loss, coef, g = OracleLossOps.anchor_loss(csr, anchor, gathered, n_edges, label, wbar, True, g_anchor)
+        if relu_gate:
+            g = torch.where(anchor > 0, g, torch.zeros_like(g))
+        return loss, coef, g
+
+    @staticmethod
+    def wsum(csr, coef, x, out=None, accumulate=False):
+        return OracleLossOps.wsum(csr, coef, x, 1.0, out if accumulate else None)

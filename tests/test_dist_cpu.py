@@ -20,7 +20,7 @@ import truth_recommendation_gnn_b200 as trg
 U, P, EE, ES, H, L = 101, 257, 2000, 500, 16, 2     # sizes that do NOT divide by the world size
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, fused=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -34,8 +34,14 @@ def _worker(rank, world, port, q):
         losses = []
         for s in range(2):
             neg = synth.synth_neg(P, EE, s)
-            losses.append(tdist.train_step_sharded(model, opt, shard, neg_p_global=neg,
-                                                   ops=oracle_ops.OracleOps, loss_ops=oracle_ops.OracleLossOps))
+            if fused:     # tape-free step with async (overlapped) collectives
+                from truth_recommendation_gnn_b200 import dist_fused
+                assert dist_fused.eligible(model, shard)
+                losses.append(dist_fused.train_step_sharded_fused(model, opt, shard, neg_p_global=neg,
+                                                                  prims=oracle_ops.OracleStepPrims))
+            else:
+                losses.append(tdist.train_step_sharded(model, opt, shard, neg_p_global=neg,
+                                                       ops=oracle_ops.OracleOps, loss_ops=oracle_ops.OracleLossOps))
         with torch.no_grad():
             out = tdist.forward_sharded(model, shard, oracle_ops.OracleOps)
         # sharded recommendation over this rank's posts
@@ -51,11 +57,12 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_sharded_train_step_and_topk_match_single_process():
-    world, port = 2, 29500 + os.getpid() % 2000
+@pytest.mark.parametrize("fused", [False, True])
+def test_sharded_train_step_and_topk_match_single_process(fused):
+    world, port = 2, 29500 + os.getpid() % 2000 + (7 if fused else 0)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, fused)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])

@@ -14,6 +14,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import truth_recommendation_gnn_b200 as trg  # noqa: E402
 from truth_recommendation_gnn_b200 import dist as tdist  # noqa: E402
+from truth_recommendation_gnn_b200 import dist_fused  # noqa: E402
 from truth_recommendation_gnn_b200 import synth  # noqa: E402
 
 
@@ -22,7 +23,8 @@ def main():
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 2e-2)):
+    for dtype, tol, fused in ((torch.float32, 2e-5, True), (torch.float32, 2e-5, False),
+                              (torch.bfloat16, 2e-2, True), (torch.bfloat16, 2e-2, False)):
         U, P, EE, ES, H, L = 20_011, 70_003, 600_000, 150_000, 128, 2
         g = synth.synth_graph(U, P, EE, ES, H, seed=0, device=dev, dtype=dtype)
         sd = synth.init_state_dict(H, H, L)
@@ -35,7 +37,11 @@ def main():
             neg = synth.synth_neg(P, EE, s, device=dev)
             l_ref = trg.train_step(ref, o_ref, g.x_dict, g.edge_index_dict, g.train_edge_index,
                                    g.interaction_type_tensor, U, P, neg_p=neg)
-            l_mod = tdist.train_step_sharded(mod, o_mod, shard, neg_p_global=neg)
+            if fused:   # tape-free step, collectives overlapped with compute
+                assert dist_fused.eligible(mod, shard)
+                l_mod = dist_fused.train_step_sharded_fused(mod, o_mod, shard, neg_p_global=neg)
+            else:       # autograd Functions + blocking collectives
+                l_mod = tdist.train_step_sharded(mod, o_mod, shard, neg_p_global=neg)
             assert abs(l_ref - l_mod) <= tol * abs(l_ref), (str(dtype), s, l_ref, l_mod)
             if s == 0:      # gradients of the first step (same weights on both sides)
                 for (n, a), (_, b) in zip(mod.named_parameters(), ref.named_parameters()):
@@ -62,7 +68,7 @@ def main():
             sv, si = tdist.recommend_sharded(q, cat_local, 100, shard.p0)
             assert torch.equal(si, ei) and torch.equal(sv, ev)
         if rank == 0:
-            print(f"dist parity ok: world={world} dtype={dtype} loss={l_mod:.6f} emb_err={err:.2e}", flush=True)
+            print(f"dist parity ok: world={world} dtype={dtype} fused={fused} loss={l_mod:.6f} emb_err={err:.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

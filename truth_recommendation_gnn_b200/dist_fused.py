@@ -1,0 +1,254 @@
+"""Tape-free, communication-overlapped train step on a destination partition.
+
+Same partitioning and the same result as ``dist.train_step_sharded`` (autograd Functions +
+blocking collectives); here the forward, the loss and the backward are ordered by hand so that
+every collective of the step is in flight while an independent kernel runs:
+
+  forward, layer l    all-gather(user rows)            ||  push partial sums over the local posts
+                      reduce-scatter(push partials)    ||  social + engages aggregation, post projection
+  loss                all-gather(final user rows)      ||  this step's negative-edge CSRs (by post, by user)
+                      reduce-scatter(dL/du partials)   ||  post-side projection backward + engages^T gather
+  backward, layer l   all-gather(d mean_direct)        ||  social^T gather
+                      reduce-scatter(d user partials)  ||  rev_engages^T gather over the local posts and
+                                                           the next (lower) layer's post-side backward
+
+Collectives are ``torch.distributed`` async ops (NCCL runs them on its own stream over NVLink /
+NVSwitch); ``wait()`` only orders the consuming kernel after them.  ReLU backward and gradient
+accumulation ride in kernel epilogues as in ``fused_step``.  ``prims`` supplies the compute
+primitives: the CUDA kernels in the product (``CUDA_STEP_PRIMS``), oracle ops in the CPU (gloo)
+tests of this host logic (``tests/oracle_ops.OracleStepPrims``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .dist import ShardedGraph, allreduce_grads
+from .graph import PushRelation
+from .nn import REL_DIRECT, REL_ENGAGE, REL_SOCIAL, StackedWeightedRGCN, WeightedRGCN
+
+
+# ------------------------------------------------------------------------------------------
+# async collectives
+# ------------------------------------------------------------------------------------------
+class _Pending:
+    """Result of an async collective: ``wait()`` orders the current stream after it."""
+
+    def __init__(self, work, out, keep=None, post=None):
+        self.work, self.out, self.keep, self.post = work, out, keep, post
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        out = self.post(self.out) if self.post is not None else self.out
+        self.keep = self.post = None
+        return out
+
+
+def all_gather_rows_async(x_local: torch.Tensor) -> _Pending:
+    world = dist.get_world_size()
+    x_local = x_local.contiguous()
+    out = torch.empty(world * x_local.size(0), *x_local.shape[1:], dtype=x_local.dtype, device=x_local.device)
+    return _Pending(dist.all_gather_into_tensor(out, x_local, async_op=True), out, keep=x_local)
+
+
+def reduce_scatter_rows_async(g_full: torch.Tensor) -> _Pending:
+    world, rank = dist.get_world_size(), dist.get_rank()
+    chunk = g_full.size(0) // world
+    g_full = g_full.contiguous()
+    if dist.get_backend() == "gloo":      # gloo has no reduce_scatter: all_reduce + slice
+        buf = g_full.clone()
+        return _Pending(dist.all_reduce(buf, async_op=True), buf,
+                        post=lambda b: b[rank * chunk:(rank + 1) * chunk].clone())
+    out = torch.empty(chunk, *g_full.shape[1:], dtype=g_full.dtype, device=g_full.device)
+    return _Pending(dist.reduce_scatter_tensor(out, g_full, op=dist.ReduceOp.SUM, async_op=True), out, keep=g_full)
+
+
+# ------------------------------------------------------------------------------------------
+# compute primitives (CUDA)
+# ------------------------------------------------------------------------------------------
+class CudaStepPrims:
+    """The sm_100a kernels, by the names the step below uses."""
+
+    @staticmethod
+    def agg_mean(rel, x_src):
+        from .fused_step import _agg
+        return _agg(rel, x_src)
+
+    @staticmethod
+    def gather_sum(rel, which, x, out=None, accumulate=False, relu_of=None):
+        from .functional import sage_agg_bwd
+        return sage_agg_bwd(rel.fwd if which == "fwd" else rel.bwd, None, x, out=out, accumulate=accumulate,
+                            relu_of=relu_of)
+
+    @staticmethod
+    def proj_fwd(terms, bias, relu):
+        from .functional import sage_proj_fwd
+        return sage_proj_fwd(terms, bias, relu)
+
+    @staticmethod
+    def proj_bwd_weight(dz, terms, want_bias):
+        from .functional import sage_proj_bwd_weight
+        return sage_proj_bwd_weight(dz, terms, want_bias)
+
+    @staticmethod
+    def proj_bwd_input(dz, terms):
+        from .functional import sage_proj_bwd_input
+        return sage_proj_bwd_input(dz, terms)
+
+    @staticmethod
+    def csr(other, key, n_key, n_other):
+        from .graph import build_csr
+        return build_csr(other, key, n_key, n_other, validate=False)
+
+    @staticmethod
+    def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate):
+        from .functional import edge_anchor_loss
+        return edge_anchor_loss(csr, anchor, gathered, n_edges, label, wbar, True, g_anchor, relu_gate=relu_gate)
+
+    @staticmethod
+    def wsum(csr, coef, x, out=None, accumulate=False):
+        from .functional import gather_wsum
+        return gather_wsum(csr, coef, x, out=out, accumulate=accumulate)
+
+
+CUDA_STEP_PRIMS = CudaStepPrims()
+
+
+def _relu_gate(g, act):
+    """ReLU backward on owned rows (1/world of a table: small next to the gather kernels)."""
+    return torch.ops.aten.threshold_backward(g, act, 0)
+
+
+def _accum(param, grad):
+    grad = grad.to(param.dtype)
+    if param.grad is None:
+        param.grad = grad
+    else:
+        param.grad.add_(grad)
+
+
+def eligible(model, shard: ShardedGraph) -> bool:
+    if type(model) not in (WeightedRGCN, StackedWeightedRGCN) or shard.world < 2 or not torch.is_grad_enabled():
+        return False
+    if not isinstance(shard.rels[REL_DIRECT], PushRelation):
+        return False
+    layers = list(model.layers) if type(model) is StackedWeightedRGCN else [model]
+    if any(conv.lin_l.bias is None for l in layers for conv in (l.msg_direct, l.msg_social, l.post_update)):
+        return False
+    return all(p.requires_grad for p in model.parameters())
+
+
+@torch.no_grad()
+def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_STEP_PRIMS):
+    """Forward + link loss + backward on this rank's partition.  Returns the LOCAL partial loss
+    (0-d); local parameter-gradient partials are accumulated into ``.grad`` (the caller all-reduces
+    both).  ``neg_p_local``: ``shard.local_negatives(neg_p)``."""
+    layers = list(model.layers) if type(model) is StackedWeightedRGCN else [model]
+    prel_d, rel_s, rel_e = shard.rels[REL_DIRECT], shard.rels[REL_SOCIAL], shard.rels[REL_ENGAGE]
+    rel_d = prel_d.rel                                  # rows ("fwd") = all users, sources = local posts
+    hu, hp = shard.x_local["user"], shard.x_local["post"]
+    n_u_pad = shard.cu * shard.world
+
+    # ---- forward ----
+    saved = []
+    for i, layer in enumerate(layers):
+        d, s, p = layer.msg_direct, layer.msg_social, layer.post_update
+        for conv, (xs, xd) in ((d, (hp, hu)), (s, (hu, hu)), (p, (hu, hp))):
+            conv.lin_l.materialize(xs.size(-1))
+            conv.lin_r.materialize(xd.size(-1))
+        wd, ws = float(layer.w_direct), float(layer.w_social)
+        ag = None if i == 0 else all_gather_rows_async(hu)
+        part = prims.gather_sum(rel_d, "fwd", hp)                       # [U_pad, F] partial sums  || all-gather
+        rs = reduce_scatter_rows_async(part)
+        del part
+        user_full = shard.layer0_sources()["user"] if i == 0 else ag.wait()
+        mean_s = prims.agg_mean(rel_s, user_full)                        # || reduce-scatter
+        mean_e = prims.agg_mean(rel_e, user_full)
+        del user_full
+        hp_n = prims.proj_fwd([(mean_e, p.lin_l.weight, 1.0), (hp, p.lin_r.weight, 1.0)], p.lin_l.bias, True)
+        mean_d = rs.wait() * prel_d.inv_deg.to(hu.dtype)[:, None]
+        w_root = wd * d.lin_r.weight + ws * s.lin_r.weight
+        b_user = wd * d.lin_l.bias + ws * s.lin_l.bias
+        hu_n = prims.proj_fwd([(mean_d, d.lin_l.weight, wd), (mean_s, s.lin_l.weight, ws), (hu, w_root, 1.0)],
+                              b_user, True)
+        saved.append((hu, hp, mean_d, mean_s, mean_e, w_root))
+        hu, hp = hu_n, hp_n
+
+    # ---- loss: every <u, p> term is evaluated by the owner of the post (dist.ShardedGraph) ----
+    ag = all_gather_rows_async(hu)
+    st = shard.loss_structures(prims)
+    neg_by_post = prims.csr(neg_p_local[0], neg_p_local[1], shard.cp, n_u_pad)      # || all-gather
+    neg_by_user = prims.csr(neg_p_local[1], neg_p_local[0], n_u_pad, shard.cp)
+    user_full = ag.wait()
+    e_glob = shard.n_pos_global
+    l_pos, c_pos, g_p = prims.anchor_loss(st["pos_by_post"], hp, user_full, e_glob, 1, shard.wbar, None, False)
+    l_neg, c_neg, dz_p = prims.anchor_loss(neg_by_post, hp, user_full, e_glob, 0, shard.wbar, g_p, True)
+    del user_full
+    g_uf = prims.wsum(st["pos_by_user"], c_pos, hp)                                 # dL/du partials, all users
+    g_uf = prims.wsum(neg_by_user, c_neg, hp, out=g_uf, accumulate=True)
+    pend_u = (reduce_scatter_rows_async(g_uf), None, hu)        # (partials in flight, local term, gate)
+    loss_local = (l_pos + l_neg).reshape(())
+    del g_uf, c_pos, c_neg, neg_by_post, neg_by_user, hu, hp
+
+    # ---- backward ----
+    for li in range(len(layers) - 1, -1, -1):
+        layer = layers[li]
+        d, s, p = layer.msg_direct, layer.msg_social, layer.post_update
+        wd, ws = float(layer.w_direct), float(layer.w_social)
+        hu_in, hp_in, mean_d, mean_s, mean_e, w_root = saved.pop()
+        # post side first: it does not depend on the user-gradient reduce-scatter still in flight
+        (dw_p, dw_pr), db_p = prims.proj_bwd_weight(dz_p, [(mean_e, 1.0), (hp_in, 1.0)], True)
+        g_uf = g_hp = None
+        if li > 0:
+            g_me, g_hp = prims.proj_bwd_input(dz_p, [(p.lin_l.weight, 1.0, rel_e.inv_deg), (p.lin_r.weight, 1.0, None)])
+            g_uf = prims.gather_sum(rel_e, "bwd", g_me)               # d user_full partials (engages^T)
+            del g_me
+        del dz_p, mean_e
+        rs, g_loc, act = pend_u
+        g = rs.wait()
+        dz_u = _relu_gate(g if g_loc is None else g_loc.add_(g), act)
+        del g, g_loc, act, pend_u
+        (dw_d, dw_s, dw_root), db_u = prims.proj_bwd_weight(dz_u, [(mean_d, wd), (mean_s, ws), (hu_in, 1.0)], True)
+        del mean_d, mean_s
+        _accum(d.lin_l.weight, dw_d)
+        _accum(s.lin_l.weight, dw_s)
+        _accum(d.lin_r.weight, wd * dw_root)
+        _accum(s.lin_r.weight, ws * dw_root)
+        _accum(d.lin_l.bias, wd * db_u)
+        _accum(s.lin_l.bias, ws * db_u)
+        _accum(p.lin_l.weight, dw_p)
+        _accum(p.lin_r.weight, dw_pr)
+        _accum(p.lin_l.bias, db_p)
+        if li == 0:
+            break
+        g_md, g_ms, g_hu = prims.proj_bwd_input(
+            dz_u, [(d.lin_l.weight, wd, prel_d.inv_deg), (s.lin_l.weight, ws, rel_s.inv_deg), (w_root, 1.0, None)])
+        del dz_u
+        ag = all_gather_rows_async(g_md)                              # every post owner needs d mean_direct
+        g_uf = prims.gather_sum(rel_s, "bwd", g_ms, out=g_uf, accumulate=True)      # || all-gather
+        pend_u = (reduce_scatter_rows_async(g_uf), g_hu, hu_in)
+        del g_uf, g_ms
+        g_md_full = ag.wait()
+        dz_p = prims.gather_sum(rel_d, "bwd", g_md_full, out=g_hp, accumulate=True, relu_of=hp_in)  # || reduce-scatter
+        del g_md_full, g_md
+    return loss_local
+
+
+def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global=None, neg_p_local=None,
+                             prims=CUDA_STEP_PRIMS, return_tensor=False):
+    """``dist.train_step_sharded`` without the tape and with the collectives overlapped."""
+    model.train()
+    optimizer.zero_grad()
+    if neg_p_local is None:
+        if neg_p_global is None:
+            neg_p_global = torch.randint(0, shard.num_posts, (shard.n_pos_global,),
+                                         device=shard.x_local["user"].device)
+        neg_p_local = shard.local_negatives(neg_p_global)
+    loss = loss_and_grads_sharded(model, shard, neg_p_local, prims).clone()
+    lw = dist.all_reduce(loss, async_op=True)
+    allreduce_grads(list(model.parameters()))
+    optimizer.step()
+    lw.wait()
+    return loss if return_tensor else loss.item()
