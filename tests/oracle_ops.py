@@ -41,7 +41,7 @@ class OracleLossOps:
     """Oracle primitives for dist.AnchoredLinkLossFn (post-owner loss partition)."""
 
     @staticmethod
-    def csr(other, key, n_key, n_other):
+    def csr(other, key, n_key, n_other, per_step=False):
         return _Csr(other, key, n_key)
 
     @staticmethod

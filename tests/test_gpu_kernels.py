@@ -275,6 +275,7 @@ def test_link_bce_deterministic(dev):
     (1000, 64, (64, 64, 64, 64), torch.float32, TOL_F32),      # tcgen05 3xTF32, 4 terms, tail tile
     (777, 128, (128, 128), torch.float32, TOL_F32),
     (128 * 200 + 5, 128, (128, 128, 128), torch.float32, TOL_F32),   # > 148 tiles: persistent loop wraps
+    (128 * 1500, 128, (128, 128), torch.float32, TOL_F32),            # ~10 tiles per CTA: every ring wraps
     (4000, 256, (256, 256), torch.float32, TOL_F32),
     (1, 64, (64, 64, 64, 64), torch.float32, TOL_F32),
     (300, 32, (16, 48), torch.float32, TOL_F32),                # not tensor-core shaped -> FMA kernel
@@ -293,6 +294,25 @@ def test_proj_fwd(dev, n, h, ks, dtype, tol):
         out = Fn.sage_proj_fwd([(A.to(dev), W.to(dev), a) for A, W, a in terms], bias.to(dev), relu)
         e = torch.relu(exp) if relu else exp
         assert_close(out.float().cpu(), e, tol, f"proj relu={relu}")
+
+
+def test_proj_fwd_kblock_signature_many_tiles(dev):
+    """Regression for a write-after-read race on the activation landing ring (a refill TMA overtook a
+    late shared-memory read once the ring ran ahead, i.e. only from a CTA's second tile on): k-block j of
+    the concatenated K contributes exactly 2^j to every output, so any k-block that is dropped, doubled
+    or taken from another pipeline stage changes the integer result."""
+    n, h, nt = 128 * 1200, 128, 2
+    rows = torch.arange(n, device=dev)
+    A = [torch.zeros(n, 128, device=dev) for _ in range(nt)]
+    for t in range(nt):
+        for j in range(4):
+            A[t][rows, 32 * j + rows % 32] = float(2 ** (t * 4 + j))
+    W = [torch.ones(h, 128, device=dev) for _ in range(nt)]
+    for _ in range(3):
+        out = Fn.sage_proj_fwd([(a, w, 1.0) for a, w in zip(A, W)], None, False)
+        assert bool((out == 255.0).all()), torch.unique(out).tolist()[:8]
+        outs = Fn.sage_proj_bwd_input(A[0], [(w, 1.0, None) for w in W])
+        assert all(bool((o == 15.0).all()) for o in outs)
 
 
 @pytest.mark.parametrize("n,h,ks,dtype,tol", [

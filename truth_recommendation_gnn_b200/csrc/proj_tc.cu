@@ -17,6 +17,7 @@
 // The tile is tall-skinny (N = hidden <= 256): the kernel is HBM-bound on the activation rows,
 // which are read exactly once; weights stay L2-resident.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -251,6 +252,257 @@ __global__ void __launch_bounds__(Cfg<F32, BN>::kThreads, 1)
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+// ---- fp32 kernel, v2: the split A operand lives in TENSOR MEMORY -----------------------------------
+// ncu on v1 (profiles/README.md, r1_v4): per 128-row tile the shared memory moves ~1.5 MB (TMA writes
+// of A + both weight planes, the split's read + two writes, and 12 operand reads of 8 KB per 32-wide
+// k-block) against 192 KB of HBM traffic: at 128 B/clk the SM's shared memory, not HBM, set the pace,
+// and a 3-stage ring (64 KB per stage) kept too few bytes in flight.  Here the split warps read the
+// TMA-landed fp32 tile once (LDS.128, swizzle-aware, conflict-free), form hi/lo in registers and write
+// them with tcgen05.st into a 4-stage ring of TMEM columns; the MMAs take A from TMEM (umma_ts) and
+// only the weight planes from shared memory.  Shared-memory traffic per tile drops to ~0.9 MB, the A
+// landing ring (5 x 16 KB, released by the split warps, not by the MMA) and the weight ring (4 x 32 KB)
+// are decoupled, and the epilogue goes through a swizzled staging tile so that every global store
+// instruction writes four full 128-byte row segments instead of 32 scattered 16-byte pieces.
+template <int BN>
+struct CfgA {
+  static constexpr int kSA = 5;                       // A landing stages (16 KB each)
+  static constexpr int kSB = 4;                       // weight stages (hi + lo planes)
+  static constexpr int kST = 4;                       // TMEM A stages (64 columns: hi | lo)
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBBytes = 2 * kBBytes;
+  static constexpr int kStagingBytes = 4 * 4096;      // one 32-row x 128-byte block per epilogue warp
+  static constexpr int kThreads = 384;
+  static constexpr int kAccCols = 2 * BN;             // double-buffered accumulator
+  static constexpr int kTmemCols = 512;               // accumulators + 4 x 64 A columns (pow2 alloc)
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kStageBBytes + kStagingBytes + 1024 + 256;
+  static_assert(kAccCols + kST * 64 <= 512, "TMEM budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CfgA<BN>::kThreads, 1)
+    proj_tc_f32a_kernel(const __grid_constant__ GemmParams p) {
+  using C = CfgA<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem_a + C::kSA * kABytes;
+  unsigned char* smem_stage = smem_b + C::kSB * C::kStageBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + C::kStagingBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_free = a_full + C::kSA;
+  uint64_t* b_full = a_free + C::kSA;
+  uint64_t* b_empty = b_full + C::kSB;
+  uint64_t* t_full = b_empty + C::kSB;
+  uint64_t* t_empty = t_full + C::kST;
+  uint64_t* acc_full = t_empty + C::kST;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (p.n_rows + BM - 1) / BM;
+
+  if (warp == 0 && lane == 0) {
+    for (int t = 0; t < p.n_a; ++t) tma_prefetch_desc(&p.a_map[t]);
+    tma_prefetch_desc(&p.b_hi_map);
+    tma_prefetch_desc(&p.b_lo_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kSA; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_free[s]), 128);
+    }
+    for (int s = 0; s < C::kSB; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    for (int s = 0; s < C::kST; ++s) {
+      mbar_init(smem_u32(&t_full[s]), 128);
+      mbar_init(smem_u32(&t_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&acc_full[a]), 1);
+      mbar_init(smem_u32(&acc_empty[a]), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a0 = tmem_base + (uint32_t)C::kAccCols;   // first A column
+
+  if (warp == 0) {
+    // ===================== TMA producer: activation tiles =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int nb = 0; nb < p.n_nblk; ++nb)
+          for (int t = 0; t < p.n_a; ++t)
+            for (int kb = 0; kb < p.a_kblocks[t]; ++kb) {
+              mbar_wait_backoff(smem_u32(&a_free[stage]), phase ^ 1);
+              const uint32_t fb = smem_u32(&a_full[stage]);
+              mbar_arrive_expect_tx(fb, kABytes);
+              tma_load_2d(smem_u32(smem_a + stage * kABytes), &p.a_map[t], fb, kb * 32, (int)(tile * BM));
+              if (++stage == C::kSA) { stage = 0; phase ^= 1; }
+            }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer: weight planes (L2-resident) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int nb = 0; nb < p.n_nblk; ++nb)
+          for (int kbt = 0; kbt < p.total_kblocks; ++kbt) {
+            mbar_wait_backoff(smem_u32(&b_empty[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&b_full[stage]);
+            mbar_arrive_expect_tx(fb, C::kStageBBytes);
+            unsigned char* dst = smem_b + stage * C::kStageBBytes;
+            tma_load_2d(smem_u32(dst), &p.b_hi_map, fb, kbt * 32, nb * BN);
+            tma_load_2d(smem_u32(dst + C::kBBytes), &p.b_lo_map, fb, kbt * 32, nb * BN);
+            if (++stage == C::kSB) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, 0, 0, BM, BN);
+      int sb = 0, st = 0, acc = 0;
+      uint32_t pb = 0, pt = 0, acc_phase = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int nb = 0; nb < p.n_nblk; ++nb) {
+          mbar_wait_backoff(smem_u32(&acc_empty[acc]), acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < p.total_kblocks; ++kb) {
+            mbar_wait_backoff(smem_u32(&t_full[st]), pt);
+            mbar_wait_backoff(smem_u32(&b_full[sb]), pb);
+            tc_fence_after();
+            const uint32_t a_hi = tmem_a0 + (uint32_t)(st * 64);
+            const uint32_t a_lo = a_hi + 32u;
+            const uint64_t b_hi = make_smem_desc_sw128(smem_u32(smem_b + sb * C::kStageBBytes), 0, 1024);
+            const uint64_t b_lo = make_smem_desc_sw128(smem_u32(smem_b + sb * C::kStageBBytes + C::kBBytes), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x (K = 8 tf32) per 32-wide k-block
+              const uint64_t o = (uint64_t)(k * 2);
+              const uint32_t c = (uint32_t)(k * 8);
+              umma_ts<true>(d, a_lo + c, b_hi + o, idesc, (kb | k) ? 1u : 0u);
+              umma_ts<true>(d, a_hi + c, b_lo + o, idesc, 1u);
+              umma_ts<true>(d, a_hi + c, b_hi + o, idesc, 1u);
+            }
+            umma_commit(smem_u32(&t_empty[st]));
+            umma_commit(smem_u32(&b_empty[sb]));
+            if (++st == C::kST) { st = 0; pt ^= 1; }
+            if (++sb == C::kSB) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(smem_u32(&acc_full[acc]));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== tf32 hi/lo split: shared memory -> registers -> TMEM =====================
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;                     // tile row == TMEM lane
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    int sa = 0, st = 0;
+    uint32_t pa = 0, pt = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int it = 0; it < p.n_nblk * p.total_kblocks; ++it) {
+        mbar_wait(smem_u32(&a_full[sa]), pa);
+        const uint32_t base = smem_u32(smem_a + sa * kABytes) + row_off;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = lds128(base + ((((uint32_t)c) ^ sw) << 4));
+          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t h = x[j] & 0xffffe000u;
+            hi[c * 4 + j] = h;
+            lo[c * 4 + j] = __float_as_uint(__uint_as_float(x[j]) - __uint_as_float(h));
+          }
+        }
+        mbar_wait(smem_u32(&t_empty[st]), pt ^ 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_a0 + lane_addr + (uint32_t)(st * 64);
+        tmem_st_32x32(ta, hi);
+        tmem_st_32x32(ta + 32u, lo);
+        // Release the landing slot only now: the stores above consume every loaded register, so the
+        // LDS have COMPLETED.  Arriving right after the LDS were merely issued let the refill TMA
+        // (async proxy) overtake a late shared-memory read: a few rows per 10^5 picked up the k-block
+        // five stages ahead (tools/debug_proj.py signature test).
+        mbar_arrive(smem_u32(&a_free[sa]));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&t_full[st]));
+        if (++sa == C::kSA) { sa = 0; pa ^= 1; }
+        if (++st == C::kST) { st = 0; pt ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: TMEM -> registers -> staging tile -> coalesced stores =====================
+    const int wq = warp & 3;
+    const uint32_t stg = smem_u32(smem_stage + wq * 4096);
+    const uint32_t sw = (uint32_t)(lane & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int nb = 0; nb < p.n_nblk; ++nb) {
+        mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
+        tc_fence_after();
+        const long long row0 = tile * BM + wq * 32;
+        const long long row = row0 + lane;
+        const float rs = (row < p.n_rows && p.row_scale[nb]) ? __ldg(p.row_scale[nb] + row) : 1.f;
+        const float* bias = p.bias[nb];
+        float* outp = reinterpret_cast<float*>(p.out[nb]);
+        const long long ld = p.ld_out[nb];
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v = __uint_as_float(r[j * 4 + q]) * rs;
+              if (bias) v += __ldg(bias + c * 32 + j * 4 + q);
+              if (p.relu) v = fmaxf(v, 0.f);
+              f[q] = v;
+            }
+            sts128(stg + (uint32_t)lane * 128u + ((((uint32_t)j) ^ sw) << 4),
+                   make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);            // row of the block, 8 lanes per row
+            const uint32_t ch = (uint32_t)(lane & 7);
+            const uint4 v = lds128(stg + (uint32_t)rr * 128u + ((ch ^ (uint32_t)(rr & 7)) << 4));
+            if (row0 + rr < p.n_rows)
+              *reinterpret_cast<uint4*>(outp + (row0 + rr) * ld + c * 32 + ch * 4) = v;
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&acc_empty[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
 // ---- weight preparation: Bcat (alpha-scaled, concatenated along K or transposed), tf32 hi / lo ----
 struct PrepArgs {
   const void* w[kMaxTerms];
@@ -342,7 +594,37 @@ int launch_cfg(const GemmParams& p, cudaStream_t st) {
   return TRG_OK;
 }
 
+template <int BN>
+int launch_cfg_a(const GemmParams& p, cudaStream_t st) {
+  using C = CfgA<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TRG_CUDA(cudaFuncSetAttribute(proj_tc_f32a_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kSmemBytes));
+    attr_set = true;
+  }
+  const long long n_tiles = (p.n_rows + BM - 1) / BM;
+  const int grid = (int)std::min<long long>(n_tiles, kNumSMs);
+  proj_tc_f32a_kernel<BN><<<grid, C::kThreads, C::kSmemBytes, st>>>(p);
+  count_launch();
+  TRG_LAUNCH_OK();
+  return TRG_OK;
+}
+
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TRG_PROJ_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int launch_gemm(const GemmParams& p, bool f32, int bn, cudaStream_t st) {
+  if (f32 && !use_v1()) {       // split A operand in tensor memory (hidden <= 128: TMEM budget)
+    if (bn == 64) return launch_cfg_a<64>(p, st);
+    if (bn == 128) return launch_cfg_a<128>(p, st);
+  }
   if (f32) {
     if (bn == 64) return launch_cfg<true, 64>(p, st);
     if (bn == 128) return launch_cfg<true, 128>(p, st);

@@ -125,7 +125,7 @@ class AnchoredLinkLossFn(torch.autograd.Function):
         want = user_full.requires_grad or post_local.requires_grad
         st = shard.loss_structures(prims)
         n_u_pad = shard.cu * shard.world
-        neg_by_post = prims.csr(neg_pairs[0], neg_pairs[1], shard.cp, n_u_pad)
+        neg_by_post = prims.csr(neg_pairs[0], neg_pairs[1], shard.cp, n_u_pad, per_step=True)
         lp, c_pos, g_p = prims.anchor_loss(st["pos_by_post"], post_local, user_full, shard.n_pos_global, 1,
                                            shard.wbar, want, None)
         ln, c_neg, g_p = prims.anchor_loss(neg_by_post, post_local, user_full, shard.n_pos_global, 0,
@@ -147,16 +147,16 @@ class AnchoredLinkLossFn(torch.autograd.Function):
             n_u_pad = shard.cu * shard.world
             # dloss/du for ALL users touched by local edges; AllGatherRows.backward reduce-scatters it
             g_user = prims.wsum(st["pos_by_user"], c_pos, post_local, g, None)
-            neg_by_user = prims.csr(neg_pairs[1], neg_pairs[0], n_u_pad, shard.cp)
+            neg_by_user = prims.csr(neg_pairs[1], neg_pairs[0], n_u_pad, shard.cp, per_step=True)
             g_user = prims.wsum(neg_by_user, c_neg, post_local, g, g_user)
         return g_user, g_post, None, None, None
 
 
 class CudaLossPrims:
     @staticmethod
-    def csr(other, key, n_key, n_other):
+    def csr(other, key, n_key, n_other, per_step=False):
         from .graph import build_csr
-        return build_csr(other, key, n_key, n_other, validate=False)
+        return build_csr(other, key, n_key, n_other, validate=False, per_step=per_step)
 
     @staticmethod
     def anchor_loss(csr, post_local, user_full, n_edges, label, wbar, want, g_post):

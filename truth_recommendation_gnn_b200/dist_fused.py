@@ -98,9 +98,9 @@ class CudaStepPrims:
         return sage_proj_bwd_input(dz, terms)
 
     @staticmethod
-    def csr(other, key, n_key, n_other):
+    def csr(other, key, n_key, n_other, per_step=False):
         from .graph import build_csr
-        return build_csr(other, key, n_key, n_other, validate=False)
+        return build_csr(other, key, n_key, n_other, validate=False, per_step=per_step)
 
     @staticmethod
     def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate):
@@ -179,8 +179,8 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     # ---- loss: every <u, p> term is evaluated by the owner of the post (dist.ShardedGraph) ----
     ag = all_gather_rows_async(hu)
     st = shard.loss_structures(prims)
-    neg_by_post = prims.csr(neg_p_local[0], neg_p_local[1], shard.cp, n_u_pad)      # || all-gather
-    neg_by_user = prims.csr(neg_p_local[1], neg_p_local[0], n_u_pad, shard.cp)
+    neg_by_post = prims.csr(neg_p_local[0], neg_p_local[1], shard.cp, n_u_pad, per_step=True)      # || all-gather
+    neg_by_user = prims.csr(neg_p_local[1], neg_p_local[0], n_u_pad, shard.cp, per_step=True)
     user_full = ag.wait()
     e_glob = shard.n_pos_global
     l_pos, c_pos, g_p = prims.anchor_loss(st["pos_by_post"], hp, user_full, e_glob, 1, shard.wbar, None, False)

@@ -272,7 +272,7 @@ class LinkBCEFn(torch.autograd.Function):
             # dloss/dp = sum over positive edges of the post (static structure) ...
             g_post = gather_wsum(ls.by_post, c_pos, user_emb, scale=g)
             # ... plus the sampled negatives, grouped by post with this step's stable sort
-            neg_csr = build_csr(pos_u, neg_p, ls.num_posts, ls.num_users, validate=False)
+            neg_csr = build_csr(pos_u, neg_p, ls.num_posts, ls.num_users, validate=False, per_step=True)
             gather_wsum(neg_csr, c_neg, user_emb, scale=g, out=g_post, accumulate=True)
         return g_user, g_post, None, None
 

@@ -112,7 +112,7 @@ def loss_and_grads(model, x_dict, edge_index_dict, train_edge_index, interaction
     l_neg, c_neg, dz_u = edge_anchor_loss(neg_by_user, hu, hp, ls.n_edges, 0, ls.wbar, True, dz_u,
                                           relu_gate=True)
     dz_p = gather_wsum(ls.by_post, c_pos, hu)
-    neg_by_post = build_csr(train_edge_index[0], neg_p, n_p, n_u, validate=False)
+    neg_by_post = build_csr(train_edge_index[0], neg_p, n_p, n_u, validate=False, per_step=True)
     gather_wsum(neg_by_post, c_neg, hu, out=dz_p, accumulate=True, relu_of=hp)
     loss = (l_pos + l_neg).reshape(())
     del col_neg, neg_by_user, neg_by_post, c_pos, c_neg, hu, hp

@@ -78,9 +78,15 @@ def _split_long_rows(csr: "CSR", t: int):
 
 
 def build_csr(other: torch.Tensor, key: torch.Tensor, n_key: int, n_other: int,
-              validate: bool = True) -> CSR:
+              validate: bool = True, per_step: bool = False) -> CSR:
     """``trg_csr_build``: stable sort of the edges by ``key``.  Bit-exact with
-    ``argsort(key, stable)`` / ``bincount`` / ``cumsum`` (oracle/csr.py)."""
+    ``argsort(key, stable)`` / ``bincount`` / ``cumsum`` (oracle/csr.py).
+
+    ``per_step``: the structure lives for one training step (this step's sampled negatives,
+    train_gnn.py:272).  Its rows are not inspected for long-row splitting: that check reads the maximum
+    degree on the host, and a host sync inside every step stops the CPU from running ahead of the GPU
+    (measured: the whole step's launch overhead then lands on the critical path at 4-8 GPUs).
+    Splitting is a load-balance measure only -- results are identical without it."""
     lib = _lib.load()
     if key.dtype != torch.int64 or other.dtype != torch.int64:
         raise TypeError("edge_index must be int64 (torch.long), as in the reference")
@@ -104,7 +110,7 @@ def build_csr(other: torch.Tensor, key: torch.Tensor, n_key: int, n_other: int,
               _lib.ptr(other) if e else None, _lib.ptr(key) if e else None, e, n_key, _lib.ptr(rowptr),
               _lib.ptr(col) if e else None, _lib.ptr(eid) if e else None, _lib.ptr(ws), ws_bytes,
               _lib.stream())
-    return CSR(rowptr, col, eid, n_key, n_other)
+    return CSR(rowptr, col, eid, n_key, n_other, False if per_step else None)
 
 
 class RelationGraph:
