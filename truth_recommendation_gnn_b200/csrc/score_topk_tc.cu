@@ -9,15 +9,18 @@
 //   warp 0   TMA: the query block once (all k-blocks resident), then catalogue tiles [N posts x H]
 //            through an mbarrier ring (SWIZZLE_128B, K-major)
 //   warp 1   one thread issues tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), accumulators
-//            double-buffered in TMEM
-//   warps 4-7 selection: thread r owns query row r; it reads its row of the accumulator tile with
-//            tcgen05.ld, compares against the running K-th best score held in a register and inserts
-//            the few survivors into its K-entry min-heap in shared memory (ordered by score desc, id
-//            asc: the stream is in ascending id order, so a tie with the K-th best never enters)
+//            double-buffered in TMEM columns [0, 256)
+//   warps 4+ selection: thread r owns query row r (= TMEM lane r); it reads its row of the accumulator
+//            tile with tcgen05.ld, rejects the whole tile with one max tree + one warp vote against the
+//            row's K-th best, pushes the few survivors to a per-thread queue in shared memory, and the
+//            warp merges full queues into the row's sorted top-K list (score desc, id asc; the stream is
+//            in ascending id order, so a tie with the K-th best never enters).  The lists live in TMEM
+//            columns [256, 512) of the row's own lane, which leaves shared memory to the catalogue ring.
 // Per-split lists go to the workspace and are merged by trg_topk_merge (also the multi-GPU merge).
 // Tensor-bound: 2*B*P*H flops against 2*P*H bytes of catalogue (AI = B = 4096 flop/B).
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -25,6 +28,12 @@ namespace trg {
 namespace tc {
 
 constexpr int kQRows = 128;
+// TMEM columns: [0,256) two accumulator tiles | [256,384) the row's top-K scores | [384,512) their ids.
+// Each query row is one TMEM lane, so a row's sorted list lives in its own lane (K <= 128): the 103 KB
+// the lists took in shared memory now hold catalogue ring stages (ablation in profiles/README.md: with
+// a 3 x 16 KB ring the TMA + MMA pipeline alone ran at 0.97 us per 128-post tile, 3.4x the MMA time).
+constexpr int kTmemColsTopk = 512;
+constexpr uint32_t kListScoreCol = 256, kListIdCol = 384;
 constexpr long long kPadIdTc = 0x7fffffffffffffffLL;
 
 struct ScoreTcParams {
@@ -33,6 +42,7 @@ struct ScoreTcParams {
   long long n_query, n_cat, id_offset;
   long long tiles_per_split;
   int k, n_splits, kblocks;   // kblocks = H / 64
+  int dbg;                    // ablation switches (TRG_TOPK_DBG): 1 = no selection, 2 = no tcgen05.ld either, 4 = no MMA
   int* thr_shared;            // [B] ordered-int keys of the best published K-th score per query row
   float* part_vals;           // [B][n_splits][k]
   long long* part_ids;        // [B][n_splits][k]
@@ -141,13 +151,31 @@ __device__ __forceinline__ int warp_merge_row(uint32_t lv_a, uint32_t li_a, uint
 }
 
 // NS = catalogue rows per ring stage (128 / 64 / 32: what fits beside Q, the lists and the queues);
-// the accumulator tile is always 128 posts wide (128 / NS stages per tile), so the selection warps
-// pay their per-tile costs (barriers, TMEM load latency) once per 128 scores.
-template <int NS, int QCAP>
-__global__ void __launch_bounds__(256, 1)
+// the accumulator tile is always 128 posts wide (128 / NS stages per tile).
+//
+// Selection runs on 4 * NPART warps: warp (wq, part) owns the TMEM lane quarter wq (query rows
+// 32 wq .. 32 wq + 31, one per lane) and the column range [part * 128/NPART, ...) of every tile, so a
+// row is scanned by NPART threads of different warps.  ncu on the one-warp-per-quarter form
+// (profiles/README.md): the tensor pipe was 16 % busy and the single selection warp of each SM
+// sub-partition issued in 15 % of its cycles -- every tcgen05.ld / vote / branch latency was exposed
+// because nothing else could issue.  With NPART warps per sub-partition the latencies overlap and a
+// tile is released after 128/NPART scores per thread instead of 128.
+//
+// Shared per-row state (the row's sorted top-K list, its length, and a 64-bit snapshot (K-th score,
+// K-th id) read with one LDS.64 per tile) is only written under a per-row lock by the warp that merges
+// a candidate queue into the list.  The snapshot a scanning thread holds may be stale, which is
+// conservative: the K-th best only improves, so nothing that belongs in the answer is ever filtered
+// out, and the merge ranks candidates exactly under (score desc, id asc).
+template <int NS, int NPART>
+__global__ void __launch_bounds__(128 + 128 * NPART, 1)
     score_topk_tc_kernel(const __grid_constant__ ScoreTcParams p, int n_stages, int list_stride) {
   constexpr int N = 128;                 // posts per accumulator tile
   constexpr int kSub = N / NS;           // ring stages per accumulator tile
+  constexpr int CW = N / NPART;          // columns scanned per thread
+  constexpr int QCAP = 32;               // per-thread candidate queue
+  constexpr int kChains = 8;             // interleaved max chains (CW / 8 sites each)
+  constexpr int kCheckEvery = N / CW;    // chains between queue-overflow checks: <= 16 pushes in between
+  constexpr int kSel = 128 * NPART;      // selection threads
   constexpr int kQStride = QCAP + 1;     // odd: lanes own consecutive rows -> conflict-free
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -156,12 +184,15 @@ __global__ void __launch_bounds__(256, 1)
   const int stage_bytes = p.kblocks * NS * 128;
   unsigned char* q_smem = smem;
   unsigned char* ring = smem + q_bytes;
-  float* lv = reinterpret_cast<float*>(ring + (size_t)n_stages * stage_bytes);
-  uint32_t* li = reinterpret_cast<uint32_t*>(lv + kQRows * list_stride);
-  float* cq_s = reinterpret_cast<float*>(li + kQRows * list_stride);          // [kQRows][kQStride]
-  uint32_t* cq_i = reinterpret_cast<uint32_t*>(cq_s + kQRows * kQStride);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-      (reinterpret_cast<uintptr_t>(cq_i + kQRows * kQStride) + 7) & ~static_cast<uintptr_t>(7));
+  float* sv = reinterpret_cast<float*>(ring + (size_t)n_stages * stage_bytes);   // merge scratch [4*NPART warps][128]
+  uint32_t* si = reinterpret_cast<uint32_t*>(sv + 4 * NPART * 128);
+  float* cq_s = reinterpret_cast<float*>(si + 4 * NPART * 128);                 // [kSel][kQStride]
+  uint32_t* cq_i = reinterpret_cast<uint32_t*>(cq_s + kSel * kQStride);
+  uint2* row_thr = reinterpret_cast<uint2*>(
+      (reinterpret_cast<uintptr_t>(cq_i + kSel * kQStride) + 7) & ~static_cast<uintptr_t>(7));   // [128] (K-th score, K-th id)
+  int* row_m = reinterpret_cast<int*>(row_thr + kQRows);                       // [128] list length
+  int* q_lock = row_m + kQRows;                                                // [4] one per TMEM lane quarter
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_lock + 4);
   uint64_t* full = bars;          // [8]
   uint64_t* empty = full + 8;     // [8]
   uint64_t* q_full = empty + 8;   // [1]
@@ -189,11 +220,17 @@ __global__ void __launch_bounds__(256, 1)
     mbar_init(smem_u32(q_full), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
-      mbar_init(smem_u32(&tmem_empty[a]), 128);
+      mbar_init(smem_u32(&tmem_empty[a]), kSel);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * N);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemColsTopk);
+  if (threadIdx.x >= 128 && threadIdx.x < 256) {      // part 0 threads: one per row
+    const int r = threadIdx.x - 128;
+    row_thr[r] = make_uint2(0xff800000u, 0xffffffffu);   // (-inf, max id): "list not full"
+    row_m[r] = 0;
+    if (r < 4) q_lock[r] = 0;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -233,9 +270,11 @@ __global__ void __launch_bounds__(256, 1)
           for (int kb = 0; kb < p.kblocks; ++kb) {
             const uint64_t qd = make_smem_desc_sw128(smem_u32(q_smem + kb * kQRows * 128), 0, 1024);
             const uint64_t cd = make_smem_desc_sw128(smem_u32(ring + (size_t)stage * stage_bytes + kb * NS * 128), 0, 1024);
+            if (!(p.dbg & 4)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss<false>(d, qd + (uint64_t)(2 * k), cd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_ss<false>(d, qd + (uint64_t)(2 * k), cd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&empty[stage]));
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -245,37 +284,100 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===================== selection: one query row per thread =====================
+    // ===================== selection: thread = (query row, column part) =====================
     const int wq = warp & 3;
+    const int part = (warp - 4) >> 2;
     const int r = wq * 32 + lane;
     const bool row_ok = q0 + r < p.n_query;
     const int K = p.k;
-    const uint32_t lv_base = smem_u32(lv), li_base = smem_u32(li);
     const uint32_t qs_base = smem_u32(cq_s), qi_base = smem_u32(cq_i);
-    const uint32_t my_qs = qs_base + 4u * (uint32_t)(r * kQStride), my_qi = qi_base + 4u * (uint32_t)(r * kQStride);
-    int m = 0;                 // entries in this row's sorted list
-    int cnt = 0;               // entries in this row's candidate queue
-    float thr = -INFINITY;     // K-th best (score, id) once the list is full
-    uint32_t kth_id = 0xffffffffu;
-    float thr_g = -INFINITY;   // best K-th score published by any catalogue split for this row
-    // merge the queues of every row of this warp holding at least `min_fill` candidates
+    const uint32_t thr_addr = smem_u32(row_thr + r);
+    const int qslot = part * kQRows + r;
+    const uint32_t my_qs = qs_base + 4u * (uint32_t)(qslot * kQStride), my_qi = qi_base + 4u * (uint32_t)(qslot * kQStride);
+    const uint32_t sv_a = smem_u32(sv + (warp - 4) * 128), si_a = smem_u32(si + (warp - 4) * 128);   // this warp's scratch
+    const uint32_t tl_s = tmem_base + ((uint32_t)(wq * 32) << 16) + kListScoreCol;   // this thread's list lane
+    const uint32_t tl_i = tmem_base + ((uint32_t)(wq * 32) << 16) + kListIdCol;
+    int cnt = 0;               // entries in this thread's candidate queue
+    // best K-th score published by any catalogue split for this row; query rows past B (zero-filled by
+    // TMA) get +inf, so nothing of theirs ever passes the filter
+    float thr_g = row_ok ? -INFINITY : INFINITY;
+    // Merge the queue of every lane holding at least `min_fill` candidates into that row's list.  The
+    // list of row L sits in TMEM lane L, reachable only by thread L of the warps of this quarter, and
+    // tcgen05.ld/st move all 32 lanes at once: the list is staged through the warp's scratch (thread L
+    // copies its 16-column chunks out), merged there by the whole warp (warp_merge_row), and written
+    // back chunk by chunk -- the other 31 threads store back the values they just loaded.  NPART > 1:
+    // the warps sharing a quarter take the quarter's lock, since a write-back rewrites every lane.
     auto drain = [&](int min_fill) {
       unsigned need = __ballot_sync(0xffffffffu, cnt >= min_fill && cnt > 0);
+      if (!need) return;
+      if (NPART > 1) {
+        if (lane == 0) {
+          while (atomicCAS(q_lock + wq, 0, 1) != 0) {
+          }
+        }
+        __syncwarp();
+        tc_fence_after();
+      }
       while (need) {
         const int L = __ffs(need) - 1;
         need &= need - 1;
         const int row = wq * 32 + L;
-        const int n_c = __shfl_sync(0xffffffffu, cnt, L), m_l = __shfl_sync(0xffffffffu, m, L);
-        const int nm = warp_merge_row(lv_base + 4u * (uint32_t)(row * list_stride), li_base + 4u * (uint32_t)(row * list_stride),
-                                      qs_base + 4u * (uint32_t)(row * kQStride), qi_base + 4u * (uint32_t)(row * kQStride),
-                                      n_c, m_l, K, lane);
-        if (lane == L) {
-          m = nm;
-          cnt = 0;
-          if (m == K) {
-            thr = __uint_as_float(lds32(lv_base + 4u * (uint32_t)(row * list_stride + K - 1)));
-            kth_id = lds32(li_base + 4u * (uint32_t)(row * list_stride + K - 1));
+        const int n_c = __shfl_sync(0xffffffffu, cnt, L);
+        asm volatile("" ::: "memory");
+        const int m_l = *reinterpret_cast<volatile int*>(row_m + row);
+#pragma unroll 1
+        for (int c = 0; c * 16 < m_l; ++c) {                 // warp-uniform trip count
+          uint32_t rs[16], ri[16];
+          tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
+          tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
+          tmem_ld_wait();
+          if (lane == L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              sts32(sv_a + 4u * (uint32_t)(c * 16 + j), rs[j]);
+              sts32(si_a + 4u * (uint32_t)(c * 16 + j), ri[j]);
+            }
           }
+        }
+        __syncwarp();
+        const uint32_t qrow = (uint32_t)((part * kQRows + row) * kQStride);
+        const int nm = warp_merge_row(sv_a, si_a, qs_base + 4u * qrow, qi_base + 4u * qrow, n_c, m_l, K, lane);
+#pragma unroll 1
+        for (int c = 0; c * 16 < nm; ++c) {
+          uint32_t rs[16], ri[16];
+          tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
+          tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
+          tmem_ld_wait();
+          if (lane == L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              rs[j] = lds32(sv_a + 4u * (uint32_t)(c * 16 + j));
+              ri[j] = lds32(si_a + 4u * (uint32_t)(c * 16 + j));
+            }
+          }
+          tmem_st_32x16(tl_s + (uint32_t)(c * 16), rs);
+          tmem_st_32x16(tl_i + (uint32_t)(c * 16), ri);
+        }
+        tmem_st_wait();
+        if (lane == L) {
+          *reinterpret_cast<volatile int*>(row_m + row) = nm;
+          if (nm == K) {
+            const uint32_t ts = lds32(sv_a + 4u * (uint32_t)(K - 1));
+            const uint32_t ti = lds32(si_a + 4u * (uint32_t)(K - 1));
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(smem_u32(row_thr + row)), "r"(ts), "r"(ti) : "memory");
+            // publish the row's K-th best to the other catalogue splits (monotone, so stale reads are safe)
+            if (q0 + row < p.n_query) atomicMax(p.thr_shared + q0 + row, float_key(__uint_as_float(ts)));
+          }
+          cnt = 0;
+        }
+        __syncwarp();
+      }
+      if (NPART > 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          atomicExch(q_lock + wq, 0);
         }
       }
     };
@@ -292,76 +394,96 @@ __global__ void __launch_bounds__(256, 1)
       tc_fence_after();
       const long long p0 = (tile0 + t) * N;                 // first post of the tile (local id)
       const long long left = p.n_cat - p0;
-      const int nvalid = left < (long long)N ? (int)left : N;
-      const uint32_t base_idx = (uint32_t)(p0 - tile0 * N);  // index relative to the split start
-      // whole accumulator row -> registers: all tcgen05.ld issued back to back, one wait
-      uint32_t v[N];
+      // valid columns of this part (catalogue tail: TMA zero-fills the rest, filtered at push time)
+      const int nvalid = (left < (long long)N ? (int)left : N) - part * CW;
+      const uint32_t base_idx = (uint32_t)(p0 - tile0 * N) + (uint32_t)(part * CW);  // relative to the split start
+      uint32_t v[CW];
+      if (p.dbg & 2) {
 #pragma unroll
-      for (int c = 0; c < N / 32; ++c)
-        tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N + c * 32), v + c * 32);
-      tmem_ld_wait();
+        for (int j = 0; j < CW; ++j) v[j] = 0xff800000u;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c)
+          tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N + part * CW + c * 32), v + c * 32);
+        tmem_ld_wait();
+      }
       // the accumulator buffer can be handed back to the MMA warp already: scores are in registers
       tc_fence_before();
       mbar_arrive(smem_u32(&tmem_empty[acc]));
       if (refresh) thr_g = fmaxf(thr_g, key_float(tg_key));
-      if (nvalid < N || !row_ok) {              // catalogue tail / query rows past B: never candidates
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-          if (j >= nvalid || !row_ok) v[j] = 0xff800000u;   // -inf
+      if (p.dbg & 1) {
+        if (v[0] == 0x12345678u) cnt = 1;   // keep the loads alive
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
       }
-      // Common case (no score of the tile can enter any list of this warp): 8 interleaved max chains,
-      // ONE warp vote, done.  Otherwise only chains holding a candidate are looked at score by score;
-      // survivors go to the row's queue, and queues are merged by the whole warp (checked after every
-      // chain = N/8 sites, so a queue of QCAP >= 2*N/8 entries cannot overflow).
-      constexpr int kChains = 2 * N / QCAP;                 // 8 (QCAP 32) or 16 (QCAP 16)
-      constexpr int kPer = N / kChains;                     // sites per chain = QCAP / 2
+      // this row's (K-th score, K-th id), one consistent 64-bit read
+      uint32_t snap_s, snap_i;
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(snap_s), "=r"(snap_i) : "r"(thr_addr) : "memory");
+      const float thr = __uint_as_float(snap_s);
+      const uint32_t kth_id = snap_i;
+      // Common case (no score of the tile can enter any list of this warp): kChains interleaved max
+      // chains, ONE warp vote, done.  Otherwise only chains holding a candidate are looked at score by
+      // score; survivors go to the thread's queue, and queues are merged by the whole warp (checked
+      // every kCheckEvery chains = at most 16 pushes, so a queue of 32 entries cannot overflow).
       float mx[kChains];
 #pragma unroll
       for (int c = 0; c < kChains; ++c) mx[c] = __uint_as_float(v[c]);
 #pragma unroll
-      for (int j = kChains; j < N; ++j) mx[j & (kChains - 1)] = fmaxf(mx[j & (kChains - 1)], __uint_as_float(v[j]));
+      for (int j = kChains; j < CW; ++j) mx[j & (kChains - 1)] = fmaxf(mx[j & (kChains - 1)], __uint_as_float(v[j]));
       float mall = mx[0];
 #pragma unroll
       for (int c = 1; c < kChains; ++c) mall = fmaxf(mall, mx[c]);
-      const float before = thr;
-      if (__any_sync(0xffffffffu, mall > -INFINITY && mall >= thr && mall >= thr_g)) {
+      if (__any_sync(0xffffffffu, mall >= thr && mall >= thr_g)) {
 #pragma unroll
         for (int c = 0; c < kChains; ++c) {
-          if (mx[c] > -INFINITY && mx[c] >= thr && mx[c] >= thr_g) {
+          if (mx[c] >= thr && mx[c] >= thr_g) {
 #pragma unroll
-            for (int j = c; j < N; j += kChains) {
+            for (int j = c; j < CW; j += kChains) {
               const float s = __uint_as_float(v[j]);
               const uint32_t id = base_idx + (uint32_t)j;
               // survivor iff it can rank before the K-th best (equal score: only with a lower id)
-              if (s > -INFINITY && s >= thr_g && (m < K || s > thr || (s == thr && id < kth_id))) {
+              if (j < nvalid && s >= thr_g && (s > thr || (s == thr && id < kth_id))) {
                 sts32(my_qs + 4u * cnt, __float_as_uint(s));
                 sts32(my_qi + 4u * cnt, id);
                 ++cnt;
               }
             }
           }
-          if (__any_sync(0xffffffffu, cnt > QCAP - kPer)) drain(QCAP - kPer + 1);
+          if ((c + 1) % kCheckEvery == 0 && __any_sync(0xffffffffu, cnt > QCAP - 16)) drain(QCAP - 16 + 1);
         }
       }
-      if (row_ok && thr > before && thr > thr_g) atomicMax(p.thr_shared + q0 + r, float_key(thr));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     drain(1);   // merge what is left in the queues
-    if (row_ok) {
-      const float* mylv = lv + r * list_stride;
-      const uint32_t* myli = li + r * list_stride;
+    asm volatile("bar.sync 1, %0;" ::"n"(kSel) : "memory");   // every part of every row has merged
+    if (part == 0) {     // every thread reads its own row's list back from its TMEM lane
+      tc_fence_after();
+      const int m = row_m[r];
       float* ov = p.part_vals + ((q0 + r) * p.n_splits + split) * K;
       long long* oi = p.part_ids + ((q0 + r) * p.n_splits + split) * K;
       const long long idbase = p.id_offset + tile0 * N;
-      for (int i = 0; i < K; ++i) {
-        ov[i] = i < m ? mylv[i] : -INFINITY;
-        oi[i] = i < m ? idbase + (long long)myli[i] : kPadIdTc;
+#pragma unroll 1
+      for (int c = 0; c * 16 < K; ++c) {
+        uint32_t rs[16], ri[16];
+        tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
+        tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i = c * 16 + j;
+            if (i < K) {
+              ov[i] = i < m ? __uint_as_float(rs[j]) : -INFINITY;
+              oi[i] = i < m ? idbase + (long long)ri[j] : kPadIdTc;
+            }
+          }
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * N);
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemColsTopk);
 }
 
 int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
@@ -376,20 +498,35 @@ bool score_tc_eligible(int hidden, int dtype, int k) {
 }
 
 constexpr int kSmemLimit = 227 * 1024;
-struct ScoreCfg { int ns, qcap, stages, smem; };
-static int fixed_smem(int hidden, int k, int qcap) {
-  return (hidden / 64) * kQRows * 128 + kQRows * (k | 1) * 8 + kQRows * (qcap + 1) * 8 + 1024 + 512;
+struct ScoreCfg { int ns, npart, stages, smem; };
+// Selection warps per TMEM lane quarter (TRG_TOPK_NPART=1|2).  Measured at config 5 (4096 x 50M, K=100):
+// 1 -> 96.8 ms, 2 -> 105-117 ms, 4 -> 137 ms.  More warps do not help because the step is not bound by
+// one warp's latency: every candidate event (about K ln(n/K) per row, ~1.5 per 128-post tile per CTA)
+// sends one warp down the slow path, and with a two-deep accumulator ring every other warp then waits
+// for it -- the tile time is the MAXIMUM over the selection warps, and more warps means more maxima.
+static int score_npart() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("TRG_TOPK_NPART");
+    v = (e && e[0] == '2') ? 2 : 1;
+  }
+  return v;
 }
-// largest ring stage (catalogue rows) and candidate queue for which >= 2 stages fit beside Q and lists
+static int fixed_smem(int hidden, int k, int npart) {
+  const int qcap = 32;
+  (void)k;   // the lists live in TMEM
+  return (hidden / 64) * kQRows * 128 + 4 * npart * 128 * 8 /*merge scratch*/ + 128 * npart * (qcap + 1) * 8 +
+         kQRows * 12 + 16 /*row state*/ + 1024 + 512;
+}
+// largest ring stage (catalogue rows) for which >= 2 stages fit beside Q, the lists and the queues
 static ScoreCfg pick_cfg(int hidden, int k) {
-  for (int qcap : {32, 16})
+  const int npart = score_npart();
+  const int fixed = fixed_smem(hidden, k, npart);
+  for (int min_stages : {4, 2})      // deep ring first (TMA latency x bandwidth), widest stage that allows it
     for (int ns : {128, 64, 32}) {
       const int stage = (hidden / 64) * ns * 128;
-      const int fixed = fixed_smem(hidden, k, qcap);
-      if (fixed + 2 * stage <= kSmemLimit) {
-        const int stages = std::min(8, (kSmemLimit - fixed) / stage);
-        return {ns, qcap, stages, fixed + stages * stage};
-      }
+      const int stages = std::min(8, (kSmemLimit - fixed) / stage);
+      if (stages >= min_stages) return {ns, npart, stages, fixed + stages * stage};
     }
   return {0, 0, 0, 0};
 }
@@ -433,6 +570,7 @@ int score_topk_tc(const void* q, const void* cat, int64_t n_query, int64_t n_cat
   rc = make_tmap_2d(&p.c_map, cat, TRG_BF16, (uint64_t)n_cat, hidden, hidden, cfg.ns);
   if (rc) return rc;
   p.n_query = n_query; p.n_cat = n_cat; p.id_offset = id_offset; p.k = k; p.kblocks = hidden / 64;
+  { const char* e = getenv("TRG_TOPK_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.n_splits = score_tc_splits(n_query, n_cat, hidden, k, &p.tiles_per_split);
   p.part_vals = reinterpret_cast<float*>(ws);
   p.part_ids = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) +
@@ -445,23 +583,23 @@ int score_topk_tc(const void* q, const void* cat, int64_t n_query, int64_t n_cat
   const int smem = cfg.smem;
   const int n_stages = cfg.stages;
   dim3 grid((unsigned)((n_query + kQRows - 1) / kQRows), (unsigned)p.n_splits);
-#define TRG_SCORE_LAUNCH(NS, QC)                                                                      \
+#define TRG_SCORE_LAUNCH(NS, NP)                                                                      \
   {                                                                                                   \
     static int set_smem = 0;                                                                          \
     if (smem > set_smem) {                                                                            \
-      TRG_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NS, QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      TRG_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<NS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       set_smem = smem;                                                                                \
     }                                                                                                 \
-    score_topk_tc_kernel<NS, QC><<<grid, 256, smem, st>>>(p, n_stages, list_stride);                  \
+    score_topk_tc_kernel<NS, NP><<<grid, 128 + 128 * NP, smem, st>>>(p, n_stages, list_stride);       \
   }
-  if (cfg.qcap == 32) {
-    if (cfg.ns == 128) TRG_SCORE_LAUNCH(128, 32)
-    else if (cfg.ns == 64) TRG_SCORE_LAUNCH(64, 32)
-    else TRG_SCORE_LAUNCH(32, 32)
+  if (cfg.npart == 2) {
+    if (cfg.ns == 128) TRG_SCORE_LAUNCH(128, 2)
+    else if (cfg.ns == 64) TRG_SCORE_LAUNCH(64, 2)
+    else TRG_SCORE_LAUNCH(32, 2)
   } else {
-    if (cfg.ns == 128) TRG_SCORE_LAUNCH(128, 16)
-    else if (cfg.ns == 64) TRG_SCORE_LAUNCH(64, 16)
-    else TRG_SCORE_LAUNCH(32, 16)
+    if (cfg.ns == 128) TRG_SCORE_LAUNCH(128, 1)
+    else if (cfg.ns == 64) TRG_SCORE_LAUNCH(64, 1)
+    else TRG_SCORE_LAUNCH(32, 1)
   }
 #undef TRG_SCORE_LAUNCH
   count_launch();
