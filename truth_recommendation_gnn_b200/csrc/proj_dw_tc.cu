@@ -8,7 +8,12 @@
 // groups).  Each persistent CTA owns a contiguous range of rows, accumulates all terms' [128 x K_t]
 // products (and the bias column sums, as one more product against a tile of ones) in TMEM over its
 // whole range, and writes one partial; a fixed-order reduction kernel sums the partials, so the
-// result is deterministic.  fp32 runs as 3xTF32 (hi/lo split of both operands in shared memory).
+// result is deterministic.  fp32 runs as 3xTF32.  The dZ^T operand (M = hidden, K = rows) is transposed and
+// split by the converter warps straight into TENSOR MEMORY (thread m reads column m of the landed dZ tile,
+// forms tf32 hi/lo in registers, tcgen05.st into lane m) and the MMAs take it from there (umma_ts); only the
+// A_t operand is split in shared memory.  ncu on the all-shared-memory form: ~212 KB of shared-memory
+// traffic per 16 rows (1.9 ms of the 2.5 ms at 5 M rows) against 1.2 ms of HBM time; the TMEM operand
+// removes the 12 x 4 KB operand reads and the dZ lo plane.
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -27,6 +32,7 @@ struct DwParams {
   int term_col[kDwMaxTerms];  // first TMEM column of each term's accumulator
   int bias_col;               // TMEM column of the bias accumulator (one 128-byte chunk wide), or -1
   int total_cols;             // columns written to the partial (terms + bias)
+  int a_col0;                 // fp32: first TMEM column of the dZ^T operand ring (32 columns per stage)
   int mblock;                 // which 128-wide block of dZ columns (hidden) this launch handles
   long long n_rows;
   long long rows_per_cta;     // multiple of KR
@@ -43,6 +49,11 @@ struct DwCfg {
   static constexpr int kThreads = 256;
 };
 
+__device__ __forceinline__ uint32_t lds32_dw(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ float tf32_rna_dw(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -95,12 +106,12 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
   const long long row1 = min(row0 + p.rows_per_cta, p.n_rows);
   const int n_kblocks = row1 > row0 ? (int)((row1 - row0 + C::KR - 1) / C::KR) : 0;
 
-  // per-stage layout: dZ hi | [dZ lo] | A_0 hi | [A_0 lo] | A_1 hi | ...
+  // per-stage layout.  bf16: dZ | A_0 | A_1 ...   fp32: dZ (raw, linear: it goes to TMEM) | A_0 hi | A_0 lo | ...
   const int plane = F32 ? 2 : 1;
   int term_off[kDwMaxTerms];
   int raw_bytes = C::kDzBytes;
   {
-    int off = plane * C::kDzBytes;
+    int off = C::kDzBytes;
     for (int t = 0; t < p.n_terms; ++t) {
       term_off[t] = off;
       const int tb = (p.term_n[t] / C::kElemsPerChunk) * C::kChunkBytes;
@@ -160,40 +171,41 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
         mbar_wait_backoff(smem_u32(F32 ? &ready[stage] : &full[stage]), phase);
         tc_fence_after();
         unsigned char* sb = smem + (size_t)stage * stage_bytes;
-        const uint32_t dz_hi = smem_u32(sb), dz_lo = smem_u32(sb + C::kDzBytes);
+        const uint32_t dz_hi = smem_u32(sb);
 #pragma unroll
         for (int ks = 0; ks < C::kKSteps; ++ks) {
           const uint32_t koff = (uint32_t)ks * (F32 ? 1024u : 2048u);  // 8 (tf32) / 16 (bf16) rows
           const uint32_t accum = (kb | ks) ? 1u : 0u;
-          const uint64_t a_hi = make_mn_desc<F32>(dz_hi + koff, lbo);
-          const uint64_t a_lo = make_mn_desc<F32>(dz_lo + koff, lbo);
+          const uint64_t a_hi = make_mn_desc<F32>(dz_hi + koff, lbo);                     // bf16 only
+          const uint32_t ta_hi = tmem_base + (uint32_t)(p.a_col0 + stage * 32 + ks * 8);  // fp32: dZ^T in TMEM
+          const uint32_t ta_lo = ta_hi + 16u;
           for (int t = 0; t < p.n_terms; ++t) {
-            const uint32_t idesc = make_idesc(F32 ? kFmtTF32 : kFmtBF16, 1, 1, 128, p.term_n[t]);
+            const uint32_t idesc = make_idesc(F32 ? kFmtTF32 : kFmtBF16, F32 ? 0 : 1, 1, 128, p.term_n[t]);
             const uint32_t tb = (uint32_t)(p.term_n[t] / C::kElemsPerChunk) * C::kChunkBytes;
             const uint32_t b_hi_addr = smem_u32(sb + term_off[t]);
             const uint64_t b_hi = make_mn_desc<F32>(b_hi_addr + koff, lbo);
             const uint32_t d = tmem_base + (uint32_t)p.term_col[t];
             if (F32) {
               const uint64_t b_lo = make_mn_desc<F32>(b_hi_addr + tb + koff, lbo);
-              umma_ss<true>(d, a_lo, b_hi, idesc, accum);
-              umma_ss<true>(d, a_hi, b_lo, idesc, 1u);
-              umma_ss<true>(d, a_hi, b_hi, idesc, 1u);
+              umma_ts<true>(d, ta_lo, b_hi, idesc, accum);
+              umma_ts<true>(d, ta_hi, b_lo, idesc, 1u);
+              umma_ts<true>(d, ta_hi, b_hi, idesc, 1u);
             } else {
               umma_ss<false>(d, a_hi, b_hi, idesc, accum);
             }
           }
-          if (p.bias_col >= 0) {
+          if (!F32 && p.bias_col >= 0) {     // fp32: the converter warps sum the columns they read anyway
             // column sums of dZ: B = a constant tile of ones, N = 16, addressed exactly like a term
             // with N = one full 128-byte chunk (MN-major, same swizzle mode; every byte of the region is 1.0)
-            const uint32_t idesc = make_idesc(F32 ? kFmtTF32 : kFmtBF16, 1, 1, 128, C::kElemsPerChunk);
+            const uint32_t idesc = make_idesc(F32 ? kFmtTF32 : kFmtBF16, F32 ? 0 : 1, 1, 128, C::kElemsPerChunk);
             // consecutive MMAs get DIFFERENT B start addresses inside the ones region: with an identical
             // B descriptor on back-to-back MMAs every other product came out with a stale B tile
             const uint64_t b1 = make_mn_desc<F32>(smem_u32(ones) + (uint32_t)ks * 4096u, 2048);
             const uint64_t b2 = make_mn_desc<F32>(smem_u32(ones) + (uint32_t)ks * 4096u + 2048u, 2048);
             const uint32_t d = tmem_base + (uint32_t)p.bias_col;
             if (F32) {
-              umma_ss<true>(d, a_lo, b1, idesc, accum);
-              umma_ss<true>(d, a_hi, b2, idesc, 1u);
+              umma_ts<true>(d, ta_lo, b1, idesc, accum);
+              umma_ts<true>(d, ta_hi, b2, idesc, 1u);
             } else {
               umma_ss<false>(d, a_hi, b1, idesc, accum);
             }
@@ -206,20 +218,40 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
     }
   } else if (warp >= 4) {
     const int tid = threadIdx.x - 128;
+    float bsum = 0.f;     // fp32: column sum of dZ[:, tid] over this CTA's rows (the bias gradient partial)
     if (F32) {
-      // ===================== tf32 hi/lo splitter (all planes of the stage) =====================
+      // ===================== tf32 converter: dZ^T -> TMEM, A_t hi/lo planes in place =====================
+      // The stage's TMEM columns were released together with its shared memory (the MMA's commit on
+      // empty[stage] precedes the TMA that filled this stage), so they can be written right away.
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t dz_col = (uint32_t)(tid >> 5) * (uint32_t)C::kChunkBytes + (uint32_t)(tid & 31) * 4u;  // column tid
       for (int kb = 0; kb < n_kblocks; ++kb) {
         mbar_wait(smem_u32(&full[stage]), phase);
         unsigned char* sb = smem + (size_t)stage * stage_bytes;
-        for (int t = -1; t < p.n_terms; ++t) {
-          const int off = t < 0 ? 0 : term_off[t];
-          const int bytes = t < 0 ? C::kDzBytes : (p.term_n[t] / C::kElemsPerChunk) * C::kChunkBytes;
-          const uint32_t hi = smem_u32(sb + off), lo = hi + (uint32_t)bytes;
+        {
+          uint32_t hi[16], lo[16];
+          const uint32_t base = smem_u32(sb) + dz_col;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const uint32_t x = lds32_dw(base + (uint32_t)r * 128u);   // dZ[row r][column tid]: a warp reads 128 contiguous bytes
+            hi[r] = x & 0xffffe000u;
+            lo[r] = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi[r]));
+            bsum += __uint_as_float(x);
+          }
+          tc_fence_after();
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p.a_col0 + stage * 32);
+          tmem_st_32x16(ta, hi);
+          tmem_st_32x16(ta + 16u, lo);
+        }
+        for (int t = 0; t < p.n_terms; ++t) {
+          const int bytes = (p.term_n[t] / C::kElemsPerChunk) * C::kChunkBytes;
+          const uint32_t hi = smem_u32(sb + term_off[t]), lo = hi + (uint32_t)bytes;
           for (int i = tid; i < bytes / 16; i += 128) split_tf32_16B(hi + (uint32_t)i * 16u, lo + (uint32_t)i * 16u);
         }
         fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(smem_u32(&ready[stage]));
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
@@ -242,6 +274,7 @@ __global__ void __launch_bounds__(256, 1) proj_dw_kernel(const __grid_constant__
                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                             __uint_as_float(r[j + 3]));
       }
+      if (F32 && p.bias_col >= 0) out[p.bias_col] = bsum;   // row wq*32+lane of the partial == column tid of dZ
     } else {
       for (int c = 0; c < p.total_cols; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(0, 0, 0, 0);
     }
@@ -283,8 +316,15 @@ __global__ void proj_dw_reduce(const DwReduceArgs a) {
   }
 }
 
+int make_tmap_mn_sw(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                    uint64_t ld_elems, uint32_t box_rows, uint32_t box_chunks, bool swizzle);
 int make_tmap_mn(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows, uint32_t box_chunks) {
+  return make_tmap_mn_sw(map, base, dtype, rows, cols, ld_elems, box_rows, box_chunks, true);
+}
+// swizzle = false: the [chunk][row][128 B] tile lands linearly (read by threads, not by the tensor core)
+int make_tmap_mn_sw(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                    uint64_t ld_elems, uint32_t box_rows, uint32_t box_chunks, bool swizzle) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -298,7 +338,8 @@ int make_tmap_mn(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dtype == TRG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                    3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   dtype == TRG_BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                            : (dtype == TRG_BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -323,16 +364,17 @@ template <bool F32>
 int launch_dw(const DwParams& p, int grid, cudaStream_t st) {
   using C = DwCfg<F32>;
   const int plane = F32 ? 2 : 1;
-  int stage_bytes = plane * C::kDzBytes;
+  int stage_bytes = C::kDzBytes;      // fp32: raw dZ only (its hi/lo go to TMEM)
   for (int t = 0; t < p.n_terms; ++t)
     stage_bytes += plane * (p.term_n[t] / C::kElemsPerChunk) * C::kChunkBytes;
   int n_stages = (int)((220 * 1024 - kOnesBytes) / stage_bytes);
   n_stages = std::min(n_stages, 8);
+  if (F32) n_stages = std::min(n_stages, (512 - p.a_col0) / 32);   // one 32-column dZ^T slot per stage
   if (n_stages < 2) {
-    set_error("proj_dw: stage of %d bytes does not fit twice in shared memory", stage_bytes);
+    set_error("proj_dw: stage of %d bytes does not fit twice in shared memory / tensor memory", stage_bytes);
     return TRG_E_UNSUPPORTED;
   }
-  int need_cols = p.total_cols, tmem_cols = 32;
+  int need_cols = F32 ? 512 : p.total_cols, tmem_cols = 32;
   while (tmem_cols < need_cols) tmem_cols <<= 1;
   const int smem = n_stages * stage_bytes + kOnesBytes + 1024 + 256;
   static int attr_smem = 0;
@@ -362,7 +404,8 @@ int proj_tc_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_term
   rows_per_cta = (rows_per_cta + kr - 1) / kr * kr;
 
   CUtensorMap dz_map, a_map[kDwMaxTerms];
-  int rc = make_tmap_mn(&dz_map, dz, dtype, (uint64_t)n_rows, hidden, hidden, kr, 128 / epc);  // chunks past hidden: OOB -> 0
+  // chunks past hidden: OOB -> 0.  fp32: linear landing layout (the converter warps read it, not the MMA)
+  int rc = make_tmap_mn_sw(&dz_map, dz, dtype, (uint64_t)n_rows, hidden, hidden, kr, 128 / epc, !f32);
   if (rc) return rc;
   for (int t = 0; t < n_terms; ++t) {
     rc = make_tmap_mn(&a_map[t], terms[t].a, dtype, (uint64_t)n_rows, terms[t].k, terms[t].k, kr,
@@ -378,7 +421,8 @@ int proj_tc_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_term
       DwReduceArgs ra{};
       p.dz_map = dz_map;
       int cols = 0, nt = 0;
-      while (t0 + nt < n_terms && nt < kDwMaxTerms && cols + terms[t0 + nt].k <= 512) {
+      const int col_cap = f32 ? 512 - 128 : 512;   // fp32 keeps 4 x 32 columns for the dZ^T operand ring
+      while (t0 + nt < n_terms && nt < kDwMaxTerms && cols + terms[t0 + nt].k <= col_cap) {
         p.a_map[nt] = a_map[t0 + nt];
         p.term_n[nt] = terms[t0 + nt].k;
         p.term_col[nt] = cols;
@@ -399,6 +443,8 @@ int proj_tc_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_term
         return TRG_E_UNSUPPORTED;
       }
       p.total_cols = cols; p.mblock = mb; p.n_rows = n_rows; p.rows_per_cta = rows_per_cta;
+      // fp32: the bias partial is summed by the converter warps, its columns exist in the partial only
+      p.a_col0 = ((f32 && p.bias_col >= 0 ? p.bias_col : cols) + 31) / 32 * 32;
       p.partial = reinterpret_cast<float*>(ws);
       rc = f32 ? launch_dw<true>(p, grid, st) : launch_dw<false>(p, grid, st);
       if (rc) return rc;
