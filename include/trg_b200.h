@@ -129,7 +129,8 @@ int trg_edge_bce_fwd(const int32_t* rowptr_u, const int32_t* col_p, const int32_
  * (anchor table), one gathered row per edge from the all-gathered user table (5x smaller than the
  * post table), one label per launch: label 1 = positive edges (loss += wbar * sum softplus(-x) / E),
  * label 0 = sampled negatives (loss += sum softplus(x) / E); E = n_edges_scale, the global positive
- * count.  loss_out[0] receives this launch's partial loss; coef_out[eid] = dloss/dx per edge;
+ * count.  loss_out[0] receives this launch's partial loss; coef_out[eid] = dloss/dx per edge (eid NULL:
+ * coef_out is written in CSR edge order, i.e. sequentially -- no scattered 4-byte stores);
  * g_anchor (+)= sum_e coef_e * gathered[col_e] (accumulate != 0 adds to the rows already there);
  * relu_gate != 0 finally zeroes g_anchor where the anchor row itself is <= 0 (the anchor table is the
  * output of the last layer's ReLU, so this is that ReLU's backward, at no extra traffic). */

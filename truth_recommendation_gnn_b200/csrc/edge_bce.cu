@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
       cp = 0; id = 0;
       if (e < e_end) {
         cp = ldg_stream(a.col_p + e);
-        id = ldg_stream(a.eid + e);
+        id = a.eid ? ldg_stream(a.eid + e) : e;   // eid == NULL: coefficients are written in CSR edge order
       }
     };
     // index pipeline: (post id, edge id) two chunks ahead, the dependent neg_p[edge id] one ahead.

@@ -146,11 +146,35 @@ class LinkStructure:
         self.n_edges = int(pos_u.numel())
         self.by_user = build_csr(pos_p, pos_u, self.num_users, self.num_posts)
         self.by_post = build_csr(pos_u, pos_p, self.num_posts, self.num_users, validate=False)
+        self._by_post_u = None
+        self._user_of_u = None
         if self.n_edges:
             w = interaction_type_tensor[pos_p + num_users].float()
             self.wbar = w.mean().reshape(1).contiguous()
         else:
             self.wbar = torch.full((1,), float("nan"), device=pos_u.device)
+
+
+    @property
+    def by_post_u(self) -> CSR:
+        """``by_post`` whose edge ids are BY-USER CSR POSITIONS instead of original edge positions, so
+        that per-edge coefficients the user-anchored loss pass wrote sequentially (in by-user order) can
+        be looked up by the post-side gather.  Static: one inverse permutation at cache-fill time."""
+        if self._by_post_u is None:
+            bu, bp = self.by_user, self.by_post
+            inv = torch.empty(self.n_edges, dtype=torch.int32, device=bu.eid.device)
+            inv[bu.eid.long()] = torch.arange(self.n_edges, dtype=torch.int32, device=bu.eid.device)
+            self._by_post_u = CSR(bp.rowptr, bp.col, inv[bp.eid.long()].contiguous(), bp.n_rows, bp.n_cols, bp._long)
+        return self._by_post_u
+
+    @property
+    def user_of_u(self) -> torch.Tensor:
+        """int64 user id of the edge at each by-user CSR position (the expanded ``by_user.rowptr``)."""
+        if self._user_of_u is None:
+            rp = self.by_user.rowptr.long()
+            self._user_of_u = torch.repeat_interleave(
+                torch.arange(self.num_users, device=rp.device), rp[1:] - rp[:-1]).contiguous()
+        return self._user_of_u
 
 
 _LINK_CACHE: dict = {}
@@ -202,10 +226,12 @@ def edge_bce_fwd(ls: LinkStructure, user_emb, post_emb, neg_p, want_grad: bool):
 
 
 def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, want_grad, g_anchor=None,
-                     relu_gate=False):
+                     relu_gate=False, coef_in_csr_order=False):
     """One launch of the single-row anchored loss: rows of ``csr`` index ``anchor``, ``csr.col`` indexes
     ``gathered``.  Returns ``(partial loss[1], coef[E_local] | None, g_anchor | None)``.  ``relu_gate``:
-    the written anchor gradient is zeroed where ``anchor <= 0`` (fused ReLU backward)."""
+    the written anchor gradient is zeroed where ``anchor <= 0`` (fused ReLU backward).
+    ``coef_in_csr_order``: ``coef[e]`` belongs to the edge at CSR position ``e`` (sequential stores) instead
+    of ``coef[csr.eid[e]]`` (original edge order, scattered 4-byte stores)."""
     lib = _lib.load()
     anchor, gathered = anchor.contiguous(), gathered.contiguous()
     _check_rows(anchor, "edge_anchor_loss")
@@ -225,7 +251,8 @@ def edge_anchor_loss(csr: CSR, anchor, gathered, n_edges_scale, label, wbar, wan
     rb = anchor.size(1) * anchor.element_size()
     nbytes = e * (rb + 12) + csr.n_rows * (rb * (2 if want_grad else 1) + 4)
     _lib.call("trg_edge_anchor_loss", nbytes, lib.trg_edge_anchor_loss,
-              _lib.ptr(csr.rowptr), _lib.ptr(csr.col) if e else None, _lib.ptr(csr.eid) if e else None,
+              _lib.ptr(csr.rowptr), _lib.ptr(csr.col) if e else None,
+              _lib.ptr(csr.eid) if (e and not coef_in_csr_order) else None,
               _lib.ptr(anchor), _lib.ptr(gathered), csr.n_rows, int(n_edges_scale), anchor.size(1),
               _lib.dtype_code(anchor.dtype), 1 if label else 0, _lib.ptr(wbar), _lib.ptr(loss), _lib.ptr(coef),
               _lib.ptr(g_anchor), 1 if (accumulate and want_grad) else 0,

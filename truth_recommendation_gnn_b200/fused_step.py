@@ -106,16 +106,21 @@ def loss_and_grads(model, x_dict, edge_index_dict, train_edge_index, interaction
     if getattr(ls, "eid_long", None) is None:
         ls.eid_long = ls.by_user.eid.long()
     bu = ls.by_user
-    col_neg = neg_p.index_select(0, ls.eid_long).int()
-    neg_by_user = CSR(bu.rowptr, col_neg, bu.eid, bu.n_rows, bu.n_cols)
-    l_pos, c_pos, dz_u = edge_anchor_loss(bu, hu, hp, ls.n_edges, 1, ls.wbar, True, None)
+    # negatives in by-user edge order; every per-edge array of the loss lives in that order from here on:
+    # the user-anchored passes write their coefficients sequentially, and the post-side gathers look them
+    # up through edge ids that ARE by-user positions (static remap for the positives; for the negatives
+    # the per-step sort is run on the by-user-ordered arrays, so its edge ids come out that way)
+    col_neg64 = neg_p.index_select(0, ls.eid_long)
+    neg_by_user = CSR(bu.rowptr, col_neg64.int(), bu.eid, bu.n_rows, bu.n_cols)
+    l_pos, c_pos, dz_u = edge_anchor_loss(bu, hu, hp, ls.n_edges, 1, ls.wbar, True, None, coef_in_csr_order=True)
     l_neg, c_neg, dz_u = edge_anchor_loss(neg_by_user, hu, hp, ls.n_edges, 0, ls.wbar, True, dz_u,
-                                          relu_gate=True)
-    dz_p = gather_wsum(ls.by_post, c_pos, hu)
-    neg_by_post = build_csr(train_edge_index[0], neg_p, n_p, n_u, validate=False, per_step=True)
+                                          relu_gate=True, coef_in_csr_order=True)
+    dz_p = gather_wsum(ls.by_post_u, c_pos, hu)
+    neg_by_post = build_csr(ls.user_of_u, col_neg64, n_p, n_u, validate=False, per_step=True)
     gather_wsum(neg_by_post, c_neg, hu, out=dz_p, accumulate=True, relu_of=hp)
+    del col_neg64
     loss = (l_pos + l_neg).reshape(())
-    del col_neg, neg_by_user, neg_by_post, c_pos, c_neg, hu, hp
+    del neg_by_user, neg_by_post, c_pos, c_neg, hu, hp
 
     # ---- backward through the layers (train_gnn.py:283) ----
     for li in range(len(layers) - 1, -1, -1):
