@@ -208,10 +208,13 @@ def gpu_train_bench(args, w, rank, world, dev):
     torch.cuda.synchronize()
 
     def step(i, e2e):
-        neg = neg_host[i % n_host].to(dev, non_blocking=True) if e2e else neg_dev[i % n_host]
+        # e2e: the pinned HOST tensor goes straight into the public API, which copies it in (on a side
+        # stream, overlapped with the forward pass: the negatives are first needed by the loss)
+        neg = neg_host[i % n_host] if e2e else neg_dev[i % n_host]
         if world > 1:
             if os.environ.get("TRG_DIST_TAPE") == "1":      # A/B: autograd Functions + blocking collectives
-                return tdist.train_step_sharded(model, opt, shard, neg_p_local=neg, return_tensor=not e2e)
+                return tdist.train_step_sharded(model, opt, shard, neg_p_local=neg.to(dev, non_blocking=True),
+                                                return_tensor=not e2e)
             return dist_fused.train_step_sharded_fused(model, opt, shard, neg_p_local=neg, return_tensor=not e2e)
         return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
                               g.interaction_type_tensor, U, P, neg_p=neg, return_tensor=not e2e)

@@ -229,6 +229,16 @@ def test_train_step_fused_and_tape_paths_agree(dev):
         lb = trg.train_step(mb, ob, g.x_dict, g.edge_index_dict, g.train_edge_index, g.interaction_type_tensor,
                             U, P, neg_p=neg, fused=False)
         assert abs(la - lb) <= TOL_F32 * abs(lb), (s, la, lb)
+    # host negatives (pinned): copied in on a side stream during the forward; same result, both paths
+    mc, md = _gpu_model(H, L, sd, dev), _gpu_model(H, L, sd, dev)
+    oc, od = torch.optim.Adam(mc.parameters(), lr=1e-3), torch.optim.Adam(md.parameters(), lr=1e-3)
+    neg = synth.synth_neg(P, 12_000, 7)
+    for fused in (True, False):
+        lc = trg.train_step(mc, oc, g.x_dict, g.edge_index_dict, g.train_edge_index, g.interaction_type_tensor,
+                            U, P, neg_p=neg.pin_memory(), fused=fused)
+        ld = trg.train_step(md, od, g.x_dict, g.edge_index_dict, g.train_edge_index, g.interaction_type_tensor,
+                            U, P, neg_p=neg.to(dev), fused=fused)
+        assert lc == ld
     # features that need a gradient (not the reference's case) fall back to the tape
     from truth_recommendation_gnn_b200 import fused_step
     xg = {k: v.clone().requires_grad_(True) for k, v in g.x_dict.items()}

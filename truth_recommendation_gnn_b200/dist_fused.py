@@ -141,7 +141,7 @@ def eligible(model, shard: ShardedGraph) -> bool:
 
 
 @torch.no_grad()
-def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_STEP_PRIMS):
+def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_STEP_PRIMS, neg_ready=None):
     """Forward + link loss + backward on this rank's partition.  Returns the LOCAL partial loss
     (0-d); local parameter-gradient partials are accumulated into ``.grad`` (the caller all-reduces
     both).  ``neg_p_local``: ``shard.local_negatives(neg_p)``."""
@@ -179,6 +179,8 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     # ---- loss: every <u, p> term is evaluated by the owner of the post (dist.ShardedGraph) ----
     ag = all_gather_rows_async(hu)
     st = shard.loss_structures(prims)
+    if neg_ready is not None:          # host negatives: their copy ran on a side stream during the forward
+        torch.cuda.current_stream().wait_event(neg_ready)
     neg_by_post = prims.csr(neg_p_local[0], neg_p_local[1], shard.cp, n_u_pad, per_step=True)      # || all-gather
     neg_by_user = prims.csr(neg_p_local[1], neg_p_local[0], n_u_pad, shard.cp, per_step=True)
     user_full = ag.wait()
@@ -246,7 +248,11 @@ def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global
             neg_p_global = torch.randint(0, shard.num_posts, (shard.n_pos_global,),
                                          device=shard.x_local["user"].device)
         neg_p_local = shard.local_negatives(neg_p_global)
-    loss = loss_and_grads_sharded(model, shard, neg_p_local, prims).clone()
+    neg_ready = None
+    if not neg_p_local.is_cuda and shard.x_local["user"].is_cuda:
+        from .train import stage_negatives
+        neg_p_local, neg_ready = stage_negatives(neg_p_local, shard.x_local["user"].device)
+    loss = loss_and_grads_sharded(model, shard, neg_p_local, prims, neg_ready=neg_ready).clone()
     lw = dist.all_reduce(loss, async_op=True)
     allreduce_grads(list(model.parameters()))
     optimizer.step()

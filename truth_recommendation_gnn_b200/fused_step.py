@@ -71,8 +71,9 @@ def _agg(rel, x):
 
 @torch.no_grad()
 def loss_and_grads(model, x_dict, edge_index_dict, train_edge_index, interaction_type_tensor, num_users,
-                   neg_p):
-    """Returns the 0-d loss tensor; parameter gradients are accumulated into ``.grad``."""
+                   neg_p, neg_ready=None):
+    """Returns the 0-d loss tensor; parameter gradients are accumulated into ``.grad``.  ``neg_ready``: an
+    event after which ``neg_p`` is valid (its host -> device copy runs on a side stream during the forward)."""
     layers = _layers(model)
     if layers is None:
         raise _lib.TrgError("loss_and_grads: model must be WeightedRGCN or StackedWeightedRGCN")
@@ -101,6 +102,8 @@ def loss_and_grads(model, x_dict, edge_index_dict, train_edge_index, interaction
 
     # ---- loss (train_gnn.py:259-281) + its backward onto the last layer's pre-activations ----
     ls = link_structure(train_edge_index, interaction_type_tensor, num_users, n_p)
+    if neg_ready is not None:
+        torch.cuda.current_stream().wait_event(neg_ready)
     if neg_p.dtype != torch.int64 or neg_p.numel() != ls.n_edges:
         raise _lib.TrgError("neg_p must be int64 with one entry per positive edge (train_gnn.py:272)")
     if getattr(ls, "eid_long", None) is None:

@@ -12,6 +12,28 @@ from . import fused_step
 from .functional import link_bce_loss, score_topk
 
 
+_COPY_STREAMS: dict = {}
+
+
+def stage_negatives(neg_p, device):
+    """This step's host input (the sampled negatives, train_gnn.py:272, when they are drawn on the host):
+    start the host -> device copy on a side stream so that it overlaps the forward pass, which does not
+    need them.  Returns ``(device tensor, event)``; the consumer waits on the event right before the loss.
+    Device tensors pass through (``event`` is None)."""
+    if neg_p is None or neg_p.is_cuda:
+        return neg_p, None
+    device = torch.device(device)
+    side = _COPY_STREAMS.get(device)
+    if side is None:
+        side = _COPY_STREAMS[device] = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(side):
+        dev_t = neg_p.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    dev_t.record_stream(torch.cuda.current_stream(device))
+    return dev_t, ev
+
+
 def train_step(model, optimizer, x_dict, edge_index_dict, train_edge_index, interaction_type_tensor,
                num_users, num_posts, neg_p=None, return_tensor=False, fused=None):
     """One full-batch step.  ``neg_p`` defaults to ``torch.randint(0, num_posts, (E,), device)`` as
@@ -25,14 +47,17 @@ def train_step(model, optimizer, x_dict, edge_index_dict, train_edge_index, inte
     model.train()
     optimizer.zero_grad()
     use_fused = fused_step.eligible(model, x_dict) if fused is None else bool(fused)
+    neg_p, neg_ready = stage_negatives(neg_p, x_dict["user"].device)     # host negatives: copy overlaps the forward
     if use_fused:
         if neg_p is None:
             neg_p = torch.randint(0, num_posts, (train_edge_index.size(1),), device=x_dict["user"].device)
         loss = fused_step.loss_and_grads(model, x_dict, edge_index_dict, train_edge_index,
-                                         interaction_type_tensor, num_users, neg_p)
+                                         interaction_type_tensor, num_users, neg_p, neg_ready=neg_ready)
     else:
         out = model(x_dict, edge_index_dict)
         user_emb, post_emb = out["user"], out["post"]
+        if neg_ready is not None:
+            torch.cuda.current_stream().wait_event(neg_ready)
         if neg_p is None:
             neg_p = torch.randint(0, num_posts, (train_edge_index.size(1),), device=user_emb.device)
         loss = link_bce_loss(user_emb, post_emb, train_edge_index, neg_p, interaction_type_tensor, num_users)
