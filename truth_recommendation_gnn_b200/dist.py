@@ -179,6 +179,14 @@ def _loss_structures(self, prims):
         n_u_pad = self.cu * self.world
         st = {"pos_by_post": prims.csr(pu, pp, self.cp, n_u_pad),
               "pos_by_user": prims.csr(pp, pu, n_u_pad, self.cp)}
+        # pos_by_user with edge ids that are BY-POST CSR POSITIONS: the post-anchored loss pass can then
+        # write its per-edge coefficients sequentially (dist_fused); static, built once
+        bp, bu = st["pos_by_post"], st["pos_by_user"]
+        if hasattr(bp, "eid") and hasattr(bu, "eid") and torch.is_tensor(getattr(bp, "eid", None)):
+            from .graph import CSR
+            inv = torch.empty(bp.eid.numel(), dtype=torch.int32, device=bp.eid.device)
+            inv[bp.eid.long()] = torch.arange(bp.eid.numel(), dtype=torch.int32, device=bp.eid.device)
+            st["pos_by_user_p"] = CSR(bu.rowptr, bu.col, inv[bu.eid.long()].contiguous(), bu.n_rows, bu.n_cols, bu._long)
         self._loss_st = st
     return st
 

@@ -103,9 +103,10 @@ class CudaStepPrims:
         return build_csr(other, key, n_key, n_other, validate=False, per_step=per_step)
 
     @staticmethod
-    def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate):
+    def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate, coef_in_csr_order=False):
         from .functional import edge_anchor_loss
-        return edge_anchor_loss(csr, anchor, gathered, n_edges, label, wbar, True, g_anchor, relu_gate=relu_gate)
+        return edge_anchor_loss(csr, anchor, gathered, n_edges, label, wbar, True, g_anchor, relu_gate=relu_gate,
+                                coef_in_csr_order=coef_in_csr_order)
 
     @staticmethod
     def wsum(csr, coef, x, out=None, accumulate=False):
@@ -185,10 +186,12 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     neg_by_user = prims.csr(neg_p_local[1], neg_p_local[0], n_u_pad, shard.cp, per_step=True)
     user_full = ag.wait()
     e_glob = shard.n_pos_global
-    l_pos, c_pos, g_p = prims.anchor_loss(st["pos_by_post"], hp, user_full, e_glob, 1, shard.wbar, None, False)
+    seq = "pos_by_user_p" in st     # positives: coefficients written in by-post order (static remap)
+    l_pos, c_pos, g_p = prims.anchor_loss(st["pos_by_post"], hp, user_full, e_glob, 1, shard.wbar, None, False,
+                                          **({"coef_in_csr_order": True} if seq else {}))
     l_neg, c_neg, dz_p = prims.anchor_loss(neg_by_post, hp, user_full, e_glob, 0, shard.wbar, g_p, True)
     del user_full
-    g_uf = prims.wsum(st["pos_by_user"], c_pos, hp)                                 # dL/du partials, all users
+    g_uf = prims.wsum(st["pos_by_user_p" if seq else "pos_by_user"], c_pos, hp)     # dL/du partials, all users
     g_uf = prims.wsum(neg_by_user, c_neg, hp, out=g_uf, accumulate=True)
     pend_u = (reduce_scatter_rows_async(g_uf), None, hu)        # (partials in flight, local term, gate)
     loss_local = (l_pos + l_neg).reshape(())
