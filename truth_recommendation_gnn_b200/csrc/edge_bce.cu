@@ -6,6 +6,8 @@
 // read ONCE per user instead of twice per edge, dloss/du is produced in the same pass without
 // atomics, and per-edge coefficients c_pos/c_neg are left for the post-side gather passes
 // (trg_gather_wsum).  HBM-bound: 2 random post rows per edge.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace trg {
@@ -281,6 +283,199 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 3 : 2) edge_bce(const Bce
   }
 }
 
+// Single-row form for 512-byte rows (fp32 H = 128, bf16 H = 256), gathered rows staged through a
+// per-warp cp.async ring.  ncu on the register form above: 5.0 TB/s of DRAM traffic, long-scoreboard
+// stalls -- a warp has its 8 row loads in flight only until they land, then reduces / exponentiates /
+// accumulates with nothing outstanding, and 80 registers cap the SM at 24 warps.  Here the row loads do
+// not occupy registers: every warp keeps two 8-edge groups (8 KB) in flight in shared memory while it
+// works on a third, so 8-16 row loads per warp are outstanding during the arithmetic as well.
+// Same arithmetic in the same order as edge_bce<T, 32, 1, 4, false>: results are bit-identical.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds128_bce(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+constexpr int kRingG = 8;                      // edges per cp.async group
+constexpr int kRingS = 16;                     // ring slots per warp (two groups)
+constexpr int kRingBytes = (kThreads / 32) * kRingS * 512;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3) edge_anchor_ring(const BceArgs a) {
+  constexpr int kVec = Elem<T>::kVec;
+  constexpr int R = 4, G = kRingG, S = kRingS;
+  constexpr unsigned full = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  __shared__ double red[2][kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ring_a = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) +
+                          (uint32_t)(warp * S * 512 + lane * 16);
+  const int64_t r0 = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * R;
+  const bool want_grad = a.g_u != nullptr;
+  float s_sum = 0.f;
+
+  if (r0 < a.n_users) {
+    const int nr = (int)((a.n_users - r0) < (int64_t)R ? (a.n_users - r0) : (int64_t)R);
+    const int my_ptr = ldg_stream(a.rowptr + r0 + min(lane, nr));
+    const int e_end = __shfl_sync(full, my_ptr, nr);
+    const int e_beg = __shfl_sync(full, my_ptr, 0);
+    const char* pb = reinterpret_cast<const char*>(a.p);
+    const char* ub = reinterpret_cast<const char*>(a.u);
+    const float wbar = __ldg(a.wbar);
+    const bool is_neg = a.label == 0;
+
+    float uf[kVec], ga[kVec];
+    uint4 u_nxt = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < kVec; ++k) ga[k] = 0.f;
+    Elem<T>::unpack(ldg_row(ub + (size_t)r0 * 512 + (size_t)lane * 16), uf);
+    if (nr > 1) u_nxt = ldg_row(ub + (size_t)(r0 + 1) * 512 + (size_t)lane * 16);
+    int cur = 0;
+    int cur_end = __shfl_sync(full, my_ptr, 1);
+
+    auto flush = [&]() {   // close anchor row `cur`: write its gradient, move to the next row
+      if (want_grad) {
+        char* ob = reinterpret_cast<char*>(a.g_u) + (size_t)(r0 + cur) * 512 + (size_t)lane * 16;
+        if (a.accumulate) {
+          float f[kVec];
+          Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob), f);
+#pragma unroll
+          for (int k = 0; k < kVec; ++k) ga[k] += f[k];
+        }
+        if (a.relu_gate) {
+#pragma unroll
+          for (int k = 0; k < kVec; ++k) ga[k] = uf[k] > 0.f ? ga[k] : 0.f;
+        }
+        stg_stream(ob, Elem<T>::pack(ga));
+      }
+      ++cur;
+      cur_end = __shfl_sync(full, my_ptr, min(cur + 1, nr));
+      Elem<T>::unpack(u_nxt, uf);
+#pragma unroll
+      for (int k = 0; k < kVec; ++k) ga[k] = 0.f;
+      if (cur + 1 < nr) u_nxt = ldg_row(ub + (size_t)(r0 + cur + 1) * 512 + (size_t)lane * 16);
+    };
+    auto load_id = [&](int ebase) -> int {          // lane l < G: gathered-row id of edge ebase + l
+      const int e = ebase + lane;
+      return (lane < G && e < e_end) ? ldg_stream(a.col_p + e) : 0;
+    };
+    auto issue = [&](int ebase, int ids, int slot0) {   // one cp.async group: rows of edges ebase .. ebase+G-1
+#pragma unroll
+      for (int q = 0; q < G; ++q) {
+        const int rid = __shfl_sync(full, ids, q);
+        if (ebase + q < e_end)
+          cp_async16(ring_a + (uint32_t)(((slot0 + q) & (S - 1)) * 512), pb + (size_t)rid * 512 + (size_t)lane * 16);
+      }
+      cp_async_commit();
+    };
+
+    {
+      const int id0 = load_id(e_beg), id1 = load_id(e_beg + G);
+      issue(e_beg, id0, 0);
+      issue(e_beg + G, id1, G);
+    }
+    int nid = load_id(e_beg + 2 * G);   // ids of the group issued at the end of the current iteration
+    int slot = 0;
+    for (int e_base = e_beg; e_base < e_end; e_base += G) {
+      const int cnt = min(G, e_end - e_base);
+      int my_id = 0;
+      if (want_grad && lane < cnt) my_id = a.eid ? ldg_stream(a.eid + e_base + lane) : e_base + lane;
+      cp_async_wait<1>();     // this group has landed (the next one may still be in flight)
+      __syncwarp();
+      float my_c = 0.f;
+      int t = 0;
+      while (t < cnt) {
+        while (e_base + t >= cur_end) flush();               // warp-uniform: next anchor row
+        const int bsz = min(cnt - t, cur_end - (e_base + t));   // a batch never straddles a row boundary
+        uint4 vp[G];
+        float v[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+          float dp = 0.f;
+          if (q < bsz) {
+            vp[q] = lds128_bce(ring_a + (uint32_t)(((slot + t + q) & (S - 1)) * 512));
+            float fp[kVec];
+            Elem<T>::unpack(vp[q], fp);
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) dp = fmaf(uf[k], fp[k], dp);
+          }
+          v[q] = dp;
+        }
+        // halving butterfly: afterwards lanes [4 j, 4 j + 4) hold the warp total of score j
+        int nv = G;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          if (nv > 1) {
+            nv >>= 1;
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+              if (i < nv) {
+                const bool hi = (lane & o) != 0;
+                const float send = hi ? v[i] : v[i + nv];
+                const float keep = hi ? v[i + nv] : v[i];
+                v[i] = keep + __shfl_xor_sync(full, send, o);
+              }
+            }
+          } else {
+            v[0] += __shfl_xor_sync(full, v[0], o);
+          }
+        }
+        constexpr int kLanesPerVal = 32 / G;
+        const int j = lane / kLanesPerVal;
+        const float z = is_neg ? v[0] : -v[0];           // loss term = softplus(z)
+        const float spv = softplus(z);
+        if ((lane % kLanesPerVal) == 0 && j < bsz) s_sum += spv;
+        if (want_grad) {
+          const float coef = (is_neg ? 1.f : -wbar) * sigmoid(z) * a.inv_e;
+#pragma unroll
+          for (int q = 0; q < G; ++q) {
+            const float cq = __shfl_sync(full, coef, q * kLanesPerVal);
+            if (q < bsz) {
+              if (lane == t + q) my_c = cq;
+              float fp[kVec];
+              Elem<T>::unpack(vp[q], fp);
+#pragma unroll
+              for (int k = 0; k < kVec; ++k) ga[k] = fmaf(cq, fp[k], ga[k]);
+            }
+          }
+        }
+        t += bsz;
+      }
+      if (want_grad && lane < cnt) a.c_pos[my_id] = my_c;
+      __syncwarp();           // every lane is done with this group's slots: refill them two groups ahead
+      const int nid_next = load_id(e_base + 3 * G);
+      issue(e_base + 2 * G, nid, slot);
+      nid = nid_next;
+      slot = (slot + G) & (S - 1);
+    }
+    while (cur < nr) flush();                               // last row and trailing empty rows
+    cp_async_wait<0>();
+  }
+
+  // deterministic CTA reduction -> one (sp, sn) pair of doubles per CTA (layout of edge_bce)
+  double dsum = s_sum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  if (lane == 0) red[0][warp] = dsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s0 += red[0][w];
+    const bool neg = a.label == 0;
+    a.partials[2 * (size_t)blockIdx.x] = neg ? 0.0 : s0;
+    a.partials[2 * (size_t)blockIdx.x + 1] = neg ? s0 : 0.0;
+  }
+}
+
 // Fixed-order final reduction: loss = wbar * mean(softplus(-pos)) + mean(softplus(neg)).
 __global__ void __launch_bounds__(1024) edge_bce_finish(const double* __restrict__ partials,
                                                         int64_t n_parts, const float* wbar,
@@ -340,6 +535,15 @@ int launch_bce(BceArgs& a, int64_t* n_blocks_out, cudaStream_t st, bool dry) {
 }  // namespace trg
 
 using namespace trg;
+
+static bool anchor_ring_off() {      // A/B switch: TRG_K4_RING=0 keeps the register form
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TRG_K4_RING");
+    v = (e && e[0] == '0') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 extern "C" size_t trg_edge_bce_workspace_bytes(int64_t n_users) {
   if (n_users < 0) return 0;
@@ -424,7 +628,21 @@ extern "C" int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, c
   a.accumulate = accumulate ? 1 : 0;
   a.relu_gate = relu_gate ? 1 : 0;
   int64_t n_blocks = 0;
-  if (n_rows > 0) {
+  if (n_rows > 0 && a.row_vecs == 32 && !anchor_ring_off()) {      // 512-byte rows: cp.async ring form
+    n_blocks = ceil_div<int64_t>(n_rows, (int64_t)(kThreads / 32) * 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+      TRG_CUDA(cudaFuncSetAttribute(edge_anchor_ring<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+      TRG_CUDA(cudaFuncSetAttribute(edge_anchor_ring<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+      attr_set = true;
+    }
+    if (dtype == TRG_F32)
+      edge_anchor_ring<float><<<(unsigned)n_blocks, kThreads, kRingBytes, st>>>(a);
+    else
+      edge_anchor_ring<__nv_bfloat16><<<(unsigned)n_blocks, kThreads, kRingBytes, st>>>(a);
+    count_launch();
+    TRG_LAUNCH_OK();
+  } else if (n_rows > 0) {
     int rc = dtype == TRG_F32 ? launch_bce<float, false>(a, &n_blocks, st, false)
                               : launch_bce<__nv_bfloat16, false>(a, &n_blocks, st, false);
     if (rc) return rc;
