@@ -227,7 +227,8 @@ def test_gather_epilogue_accumulate_and_relu_gate(dev, f, dtype, tol, long_rows,
 # ---------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("h,dtype,tol", [(64, torch.float32, TOL_F32), (128, torch.float32, TOL_F32),
                                          (16, torch.float32, TOL_F32), (256, torch.float32, TOL_F32),
-                                         (128, torch.bfloat16, TOL_BF16)])
+                                         (128, torch.bfloat16, TOL_BF16),
+                                         (256, torch.bfloat16, TOL_BF16)])   # 512-byte bf16 rows: cp.async ring form
 def test_link_bce_fwd_bwd(dev, h, dtype, tol):
     U, P, E = 300, 500, 4000
     g = torch.Generator().manual_seed(h)

@@ -20,6 +20,7 @@
 // Tensor-bound: 2*B*P*H flops against 2*P*H bytes of catalogue (AI = B = 4096 flop/B).
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -333,9 +334,9 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
           tmem_ld_wait();
           if (lane == L) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              sts32(sv_a + 4u * (uint32_t)(c * 16 + j), rs[j]);
-              sts32(si_a + 4u * (uint32_t)(c * 16 + j), ri[j]);
+            for (int j = 0; j < 16; j += 4) {
+              sts128(sv_a + 4u * (uint32_t)(c * 16 + j), make_uint4(rs[j], rs[j + 1], rs[j + 2], rs[j + 3]));
+              sts128(si_a + 4u * (uint32_t)(c * 16 + j), make_uint4(ri[j], ri[j + 1], ri[j + 2], ri[j + 3]));
             }
           }
         }
@@ -350,9 +351,11 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
           tmem_ld_wait();
           if (lane == L) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              rs[j] = lds32(sv_a + 4u * (uint32_t)(c * 16 + j));
-              ri[j] = lds32(si_a + 4u * (uint32_t)(c * 16 + j));
+            for (int j = 0; j < 16; j += 4) {
+              const uint4 a4 = lds128(sv_a + 4u * (uint32_t)(c * 16 + j));
+              const uint4 b4 = lds128(si_a + 4u * (uint32_t)(c * 16 + j));
+              rs[j] = a4.x; rs[j + 1] = a4.y; rs[j + 2] = a4.z; rs[j + 3] = a4.w;
+              ri[j] = b4.x; ri[j + 1] = b4.y; ri[j + 2] = b4.z; ri[j + 3] = b4.w;
             }
           }
           tmem_st_32x16(tl_s + (uint32_t)(c * 16), rs);
@@ -383,7 +386,11 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
     };
     int acc = 0;
     uint32_t acc_phase = 0;
+    // TRG_TOPK_DBG & 8: cycle accounting of the selection loop (printed by CTA (0,0))
+    const bool prof = (p.dbg & 8) != 0;
+    long long c_wait = 0, c_ld = 0, c_fast = 0, c_slow = 0, n_slow = 0, n_drain = 0, c_drain = 0, tk = 0;
     for (int t = 0; t < n_tiles; ++t) {
+      if (prof) tk = clock64();
       // Threshold published by the other catalogue splits for this query row: the K-th best of ANY
       // subset is a lower bound of the global K-th best, so scores strictly below it can never be in
       // the answer (ties with it are decided locally).  Refreshed every 16 tiles, off the critical path.
@@ -392,24 +399,49 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
       if (refresh) tg_key = __ldcg(p.thr_shared + q0 + r);
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
+      if (prof) { const long long n = clock64(); c_wait += n - tk; tk = n; }
       const long long p0 = (tile0 + t) * N;                 // first post of the tile (local id)
       const long long left = p.n_cat - p0;
       // valid columns of this part (catalogue tail: TMA zero-fills the rest, filtered at push time)
       const int nvalid = (left < (long long)N ? (int)left : N) - part * CW;
       const uint32_t base_idx = (uint32_t)(p0 - tile0 * N) + (uint32_t)(part * CW);  // relative to the split start
+      // accumulator row -> registers, 32 columns at a time, with the running maxima of chunk c-1 taken
+      // while chunk c is in flight (cycle accounting, TRG_TOPK_DBG=8: the four loads issued back to back
+      // cost ~420 clocks per tile on their own, as much as the rest of the fast path and the MMA)
       uint32_t v[CW];
+      float mx[kChains];
+      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N + part * CW);
       if (p.dbg & 2) {
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] = 0xff800000u;
-      } else {
 #pragma unroll
-        for (int c = 0; c < CW / 32; ++c)
-          tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N + part * CW + c * 32), v + c * 32);
+        for (int c = 0; c < kChains; ++c) mx[c] = -INFINITY;
+      } else {
+        tmem_ld_32x32(t_row, v);
         tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) mx[c] = __uint_as_float(v[c]);
+#define TRG_TOPK_MAX_CHUNK(CH, J0)                                                              \
+  _Pragma("unroll") for (int j = (J0); j < 32; ++j)                                             \
+      mx[j & (kChains - 1)] = fmaxf(mx[j & (kChains - 1)], __uint_as_float(v[(CH) * 32 + j]));
+        if (CW > 32) tmem_ld_32x32(t_row + 32u, v + 32);
+        TRG_TOPK_MAX_CHUNK(0, kChains)
+        if (CW > 32) tmem_ld_wait();
+        if (CW > 64) tmem_ld_32x32(t_row + 64u, v + 64);
+        if (CW > 32) { TRG_TOPK_MAX_CHUNK(1, 0) }
+        if (CW > 64) tmem_ld_wait();
+        if (CW > 96) tmem_ld_32x32(t_row + 96u, v + 96);
+        if (CW > 64) { TRG_TOPK_MAX_CHUNK(2, 0) }
+        if (CW > 96) {
+          tmem_ld_wait();
+          TRG_TOPK_MAX_CHUNK(3, 0)
+        }
+#undef TRG_TOPK_MAX_CHUNK
       }
       // the accumulator buffer can be handed back to the MMA warp already: scores are in registers
       tc_fence_before();
       mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (prof) { const long long n = clock64(); c_ld += n - tk; tk = n; }
       if (refresh) thr_g = fmaxf(thr_g, key_float(tg_key));
       if (p.dbg & 1) {
         if (v[0] == 0x12345678u) cnt = 1;   // keep the loads alive
@@ -425,15 +457,12 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
       // chains, ONE warp vote, done.  Otherwise only chains holding a candidate are looked at score by
       // score; survivors go to the thread's queue, and queues are merged by the whole warp (checked
       // every kCheckEvery chains = at most 16 pushes, so a queue of 32 entries cannot overflow).
-      float mx[kChains];
-#pragma unroll
-      for (int c = 0; c < kChains; ++c) mx[c] = __uint_as_float(v[c]);
-#pragma unroll
-      for (int j = kChains; j < CW; ++j) mx[j & (kChains - 1)] = fmaxf(mx[j & (kChains - 1)], __uint_as_float(v[j]));
       float mall = mx[0];
 #pragma unroll
       for (int c = 1; c < kChains; ++c) mall = fmaxf(mall, mx[c]);
-      if (__any_sync(0xffffffffu, mall >= thr && mall >= thr_g)) {
+      const bool any_cand = __any_sync(0xffffffffu, mall >= thr && mall >= thr_g);
+      if (prof) { const long long n = clock64(); c_fast += n - tk; tk = n; }
+      if (any_cand) {
 #pragma unroll
         for (int c = 0; c < kChains; ++c) {
           if (mx[c] >= thr && mx[c] >= thr_g) {
@@ -449,11 +478,22 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
               }
             }
           }
-          if ((c + 1) % kCheckEvery == 0 && __any_sync(0xffffffffu, cnt > QCAP - 16)) drain(QCAP - 16 + 1);
+          if ((c + 1) % kCheckEvery == 0 && __any_sync(0xffffffffu, cnt > QCAP - 16)) {
+            long long td = 0;
+            if (prof) td = clock64();
+            drain(QCAP - 16 + 1);
+            if (prof) { c_drain += clock64() - td; ++n_drain; }
+          }
         }
+        if (prof) { const long long n = clock64(); c_slow += n - tk; tk = n; ++n_slow; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+      printf("sel warp %d: tiles %d | cycles/tile: wait %.0f ld %.0f fast %.0f slow %.0f (of which drain %.0f) | slow tiles %.3f/tile drains %.4f/tile, %.0f cyc/slow %.0f cyc/drain\n",
+             warp, n_tiles, (double)c_wait / n_tiles, (double)c_ld / n_tiles, (double)c_fast / n_tiles,
+             (double)c_slow / n_tiles, (double)c_drain / n_tiles, (double)n_slow / n_tiles, (double)n_drain / n_tiles,
+             n_slow ? (double)c_slow / n_slow : 0.0, n_drain ? (double)c_drain / n_drain : 0.0);
     drain(1);   // merge what is left in the queues
     asm volatile("bar.sync 1, %0;" ::"n"(kSel) : "memory");   // every part of every row has merged
     if (part == 0) {     // every thread reads its own row's list back from its TMEM lane
