@@ -669,12 +669,16 @@ __global__ void __launch_bounds__(384, 1)
     int head = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool prof = (p.dbg & 8) != 0;      // cycle accounting, printed by CTA (0,0)
+    long long c_wait = 0, c_ld = 0, c_fast = 0, c_ev = 0, n_ev = 0, tk = 0, c_e1 = 0, c_e2 = 0, c_e3 = 0;
     for (int t = 0; t < n_tiles; ++t) {
+      if (prof) tk = clock64();
       int tg_key = 0;
       const bool refresh = (t & 15) == 0 && row_ok;
       if (refresh) tg_key = __ldcg(p.thr_shared + q0 + r);
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
+      if (prof) { const long long n = clock64(); c_wait += n - tk; tk = n; }
       const long long p0 = (tile0 + t) * N;
       const long long left = p.n_cat - p0;
       const int nvalid = left < (long long)N ? (int)left : N;
@@ -691,6 +695,7 @@ __global__ void __launch_bounds__(384, 1)
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tmem_empty[acc]));      // scores are in registers: hand the buffer back
+      if (prof) { const long long n = clock64(); c_ld += n - tk; tk = n; }
       if (refresh) {
         thr_g = fmaxf(thr_g, key_float(tg_key));
         row_tg[r] = thr_g;                           // the helper filters with it too
@@ -713,6 +718,7 @@ __global__ void __launch_bounds__(384, 1)
       for (int c = 1; c < kChains; ++c) mall = fmaxf(mall, mx[c]);
       const bool cand = mall >= thr && mall >= thr_g;
       const unsigned mask = __ballot_sync(0xffffffffu, cand);
+      if (prof) { const long long n = clock64(); c_fast += n - tk; tk = n; }
       // every lane with a candidate hands its whole row of the tile to the helper; when more lanes have
       // one than the ring has free slots (the first tiles: every list is still empty) they go in rounds
       unsigned rem = mask;
@@ -723,6 +729,8 @@ __global__ void __launch_bounds__(384, 1)
           }
         }
         space = __shfl_sync(0xffffffffu, space, 0);
+        long long te = 0;
+        if (prof) { te = clock64(); c_e1 += te - tk; }
         const bool pending = (rem >> lane) & 1u;
         const int k = __popc(rem & ((1u << lane) - 1u));
         const bool go = pending && k < space;
@@ -733,14 +741,23 @@ __global__ void __launch_bounds__(384, 1)
           sts128(sa + (uint32_t)(N * 4), make_uint4((uint32_t)lane, base_idx, (uint32_t)nvalid, 0u));
         }
         __syncwarp();
+        if (prof) { const long long n = clock64(); c_e2 += n - te; te = n; }
         head += min(__popc(rem), space);
         if (lane == 0) {
-          __threadfence_block();
+          if (!(p.dbg & 16)) __threadfence_block();
           *c_head = head;
         }
+        if (prof) { const long long n = clock64(); c_e3 += n - te; }
         rem = __ballot_sync(0xffffffffu, pending && !go);
       }
+      if (prof && mask) { c_ev += clock64() - tk; ++n_ev; }
     }
+    if (prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+      printf("scan warp %d: tiles %d | cycles/tile: wait %.0f ld %.0f fast %.0f hand-off %.0f | hot tiles %.3f/tile, %.0f cyc each "
+             "(ring space %.0f, copy %.0f, publish %.0f)\n",
+             warp, n_tiles, (double)c_wait / n_tiles, (double)c_ld / n_tiles, (double)c_fast / n_tiles,
+             (double)c_ev / n_tiles, (double)n_ev / n_tiles, n_ev ? (double)c_ev / n_ev : 0.0,
+             n_ev ? (double)c_e1 / n_ev : 0.0, n_ev ? (double)c_e2 / n_ev : 0.0, n_ev ? (double)c_e3 / n_ev : 0.0);
     __syncwarp();
     if (lane == 0) {
       __threadfence_block();
