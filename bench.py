@@ -306,7 +306,8 @@ def gpu_topk_bench(args, dev, n_post=50_000_000, hidden=128, k=100, batch=4096, 
                 roofline=dict(bound="tensor", achieved=tf, peak=pk["bf16_tflops"], unit="TFLOP/s",
                               frac=tf / pk["bf16_tflops"], peak_source=pk["source"]),
                 batch=batch, n_post=n_post, hidden=hidden, k=k, dtype="bf16 in / fp32 accumulate",
-                kernel="score_topk_tc_kernel (tcgen05 kind::f16 + TMEM row scan + warp-cooperative top-k merge)")
+                kernel="score_topk_tc2_kernel (tcgen05 kind::f16; scan warps read TMEM rows, helper warps keep the "
+                       "top-K lists in TMEM)")
 
 
 def main():

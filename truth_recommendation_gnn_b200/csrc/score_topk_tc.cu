@@ -538,14 +538,24 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
 //              queue and merge full queues into the row's list in TMEM.  Only the helper touches queues
 //              and lists, so there are no locks; the scan warps filter with a snapshot that may be stale
 //              (conservative), the helper ranks exactly, in stream order (= ascending id).
+//
+// Tried and measured (config 5): the query block as a TMEM-resident A operand (QT = true: copied once with
+// tcgen05.st, MMAs issued as umma_ts) with 96-post tiles so that accumulators (2 x 96), lists (2 x 128) and Q
+// (64 columns) fit the 512 TMEM columns.  Exact (all top-k tests pass) but no faster than Q in shared memory
+// at the same tile width (89.6 vs 89.7 ms), and 96-post tiles cost 15 % against 128-post ones (74 - 78 ms):
+// the slow shared-memory stores of the hand-off (~30 cycles per STS.128) are NOT caused by the MMA's operand
+// reads.  The product therefore runs 128-post tiles with Q in shared memory; the QT path stays compiled for
+// kTileN2 = 96 builds.
 constexpr int kSlotRing = 8;                 // slots per quarter
-constexpr int kSlotWords = 136;              // 128 scores + header (lane, base index, valid columns), 16 B aligned
+constexpr int kTileN2 = 128;                 // posts per accumulator tile
+constexpr int kSlotWords = kTileN2 + 4;      // scores + header (lane, base index, valid columns), 16 B aligned
 constexpr int kQCap2 = 32;
+constexpr uint32_t kListScoreCol2 = 2 * kTileN2, kListIdCol2 = kListScoreCol2 + 128, kQCol2 = kListIdCol2 + 128;
 
-template <int NS>
+template <int NS, bool QT>
 __global__ void __launch_bounds__(384, 1)
     score_topk_tc2_kernel(const __grid_constant__ ScoreTcParams p, int n_stages) {
-  constexpr int N = 128;
+  constexpr int N = kTileN2;
   constexpr int kSub = N / NS;
   constexpr int kChains = 8;
   constexpr int kQStride = kQCap2 + 1;
@@ -571,7 +581,8 @@ __global__ void __launch_bounds__(384, 1)
   uint64_t* q_full = empty + 8;   // [1]
   uint64_t* tmem_full = q_full + 1;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* q_tmem = tmem_empty + 2;     // [1] Q copied into tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_tmem + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q0 = (long long)blockIdx.x * kQRows;
@@ -591,6 +602,7 @@ __global__ void __launch_bounds__(384, 1)
       mbar_init(smem_u32(&empty[s]), 1);
     }
     mbar_init(smem_u32(q_full), 1);
+    mbar_init(smem_u32(q_tmem), 128);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
       mbar_init(smem_u32(&tmem_empty[a]), 128);
@@ -629,7 +641,12 @@ __global__ void __launch_bounds__(384, 1)
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kFmtBF16, 0, 0, kQRows, NS);
-      mbar_wait(smem_u32(q_full), 0);
+      if (QT) {
+        mbar_wait(smem_u32(q_tmem), 0);
+        tc_fence_after();
+      } else {
+        mbar_wait(smem_u32(q_full), 0);
+      }
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
@@ -644,8 +661,13 @@ __global__ void __launch_bounds__(384, 1)
             const uint64_t cd = make_smem_desc_sw128(smem_u32(ring + (size_t)stage * stage_bytes + kb * NS * 128), 0, 1024);
             if (!(p.dbg & 4)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ss<false>(d, qd + (uint64_t)(2 * k), cd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (QT)     // Q from tensor memory: 64 bf16 of a k-block = 32 columns, 16 per MMA = 8 columns
+                  umma_ts<false>(d, tmem_base + kQCol2 + (uint32_t)(kb * 32 + k * 8), cd + (uint64_t)(2 * k), idesc,
+                                 (kb | k) ? 1u : 0u);
+                else
+                  umma_ss<false>(d, qd + (uint64_t)(2 * k), cd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              }
             }
           }
           umma_commit(smem_u32(&empty[stage]));
@@ -666,6 +688,24 @@ __global__ void __launch_bounds__(384, 1)
     volatile int* c_tail = ctl + wq * 4 + 1;
     volatile int* c_done = ctl + wq * 4 + 2;
     float thr_g = row_ok ? -INFINITY : INFINITY;   // rows past B (zero-filled by TMA) never produce candidates
+    if (QT) {
+      // query block: shared memory (SWIZZLE_128B, K-major) -> this thread's TMEM lane; the 32-bit words go over
+      // as they are (bf16 pair k, k+1 of the row = one A-operand column)
+      mbar_wait(smem_u32(q_full), 0);
+      const uint32_t qrow = smem_u32(q_smem) + (uint32_t)r * 128u;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 x = lds128(qrow + (uint32_t)(kb * kQRows * 128) + ((((uint32_t)c) ^ ((uint32_t)r & 7u)) << 4));
+          w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+        }
+        tmem_st_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + kQCol2 + (uint32_t)(kb * 32), w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(q_tmem));
+    }
     int head = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -769,8 +809,8 @@ __global__ void __launch_bounds__(384, 1)
     const int K = p.k;
     const uint32_t qs_base = smem_u32(cq_s), qi_base = smem_u32(cq_i);
     const uint32_t sv_a = smem_u32(sv + wq * 128), si_a = smem_u32(si + wq * 128);
-    const uint32_t tl_s = tmem_base + ((uint32_t)(wq * 32) << 16) + kListScoreCol;
-    const uint32_t tl_i = tmem_base + ((uint32_t)(wq * 32) << 16) + kListIdCol;
+    const uint32_t tl_s = tmem_base + ((uint32_t)(wq * 32) << 16) + kListScoreCol2;
+    const uint32_t tl_i = tmem_base + ((uint32_t)(wq * 32) << 16) + kListIdCol2;
     const uint32_t slot_base = smem_u32(slots + wq * kSlotRing * kSlotWords);
     volatile int* c_head = ctl + wq * 4 + 0;
     volatile int* c_tail = ctl + wq * 4 + 1;
@@ -982,9 +1022,11 @@ static ScoreCfg pick_cfg(int hidden, int k) {
   return {0, 0, 0, 0};
 }
 
+static bool score_v1();
 int score_tc_splits(int64_t n_query, int64_t n_cat, int hidden, int k, long long* tiles_per_split) {
   (void)hidden; (void)k;
-  const int64_t n_tiles = (n_cat + 127) / 128;
+  const int64_t tile = score_v1() ? 128 : kTileN2;
+  const int64_t n_tiles = (n_cat + tile - 1) / tile;
   const int64_t q_blocks = (n_query + kQRows - 1) / kQRows;
   int64_t s = std::max<int64_t>(1, kNumSMs / q_blocks);
   s = std::min<int64_t>(s, std::max<int64_t>(1, n_tiles / 8));   // at least ~8 tiles per split
@@ -1008,7 +1050,7 @@ static int fixed_smem2(int hidden) {
 static ScoreCfg pick_cfg2(int hidden) {
   const int fixed = fixed_smem2(hidden);
   for (int min_stages : {4, 2})
-    for (int ns : {128, 64, 32}) {
+    for (int ns : {kTileN2, kTileN2 / 2}) {
       const int stage = (hidden / 64) * ns * 128;
       const int stages = std::min(8, (kSmemLimit - fixed) / stage);
       if (stages >= min_stages) return {ns, 1, stages, fixed + stages * stage};
@@ -1065,19 +1107,20 @@ int score_topk_tc(const void* q, const void* cat, int64_t n_query, int64_t n_cat
     }                                                                                                 \
     score_topk_tc_kernel<NS, NP><<<grid, 128 + 128 * NP, smem, st>>>(p, n_stages, list_stride);       \
   }
-#define TRG_SCORE_LAUNCH2(NS)                                                                         \
+#define TRG_SCORE_LAUNCH2(NS, QT)                                                                     \
   {                                                                                                   \
     static int set_smem = 0;                                                                          \
     if (smem > set_smem) {                                                                            \
-      TRG_CUDA(cudaFuncSetAttribute(score_topk_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      TRG_CUDA(cudaFuncSetAttribute(score_topk_tc2_kernel<NS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       set_smem = smem;                                                                                \
     }                                                                                                 \
-    score_topk_tc2_kernel<NS><<<grid, 384, smem, st>>>(p, n_stages);                                  \
+    score_topk_tc2_kernel<NS, QT><<<grid, 384, smem, st>>>(p, n_stages);                              \
   }
   if (!score_v1()) {
-    if (cfg.ns == 128) TRG_SCORE_LAUNCH2(128)
-    else if (cfg.ns == 64) TRG_SCORE_LAUNCH2(64)
-    else TRG_SCORE_LAUNCH2(32)
+    // Q operand in tensor memory: only when it fits beside accumulators and lists (kTileN2 = 96 builds)
+    const bool qt = (int)kQCol2 + 64 <= kTmemColsTopk && hidden <= 128 && !getenv("TRG_TOPK_QSMEM");
+    if (cfg.ns == kTileN2) { if (qt) TRG_SCORE_LAUNCH2(kTileN2, true) else TRG_SCORE_LAUNCH2(kTileN2, false) }
+    else { if (qt) TRG_SCORE_LAUNCH2(kTileN2 / 2, true) else TRG_SCORE_LAUNCH2(kTileN2 / 2, false) }
   } else if (cfg.npart == 2) {
     if (cfg.ns == 128) TRG_SCORE_LAUNCH(128, 2)
     else if (cfg.ns == 64) TRG_SCORE_LAUNCH(64, 2)
