@@ -20,8 +20,8 @@ def stage_negatives(neg_p, device):
     start the host -> device copy on a side stream so that it overlaps the forward pass, which does not
     need them.  Returns ``(device tensor, event)``; the consumer waits on the event right before the loss.
     Device tensors pass through (``event`` is None)."""
-    if neg_p is None or neg_p.is_cuda:
-        return neg_p, None
+    if neg_p is None or neg_p.is_cuda or torch.device(device).type != "cuda":
+        return neg_p, None       # (host features: the model itself raises TrgError -- there is no CPU path)
     device = torch.device(device)
     side = _COPY_STREAMS.get(device)
     if side is None:
