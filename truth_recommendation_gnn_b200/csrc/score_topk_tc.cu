@@ -424,15 +424,15 @@ __global__ void __launch_bounds__(128 + 128 * NPART, 1)
 #define TRG_TOPK_MAX_CHUNK(CH, J0)                                                              \
   _Pragma("unroll") for (int j = (J0); j < 32; ++j)                                             \
       mx[j & (kChains - 1)] = fmaxf(mx[j & (kChains - 1)], __uint_as_float(v[(CH) * 32 + j]));
-        if (CW > 32) tmem_ld_32x32(t_row + 32u, v + 32);
+        if constexpr (CW > 32) tmem_ld_32x32(t_row + 32u, v + 32);
         TRG_TOPK_MAX_CHUNK(0, kChains)
-        if (CW > 32) tmem_ld_wait();
-        if (CW > 64) tmem_ld_32x32(t_row + 64u, v + 64);
-        if (CW > 32) { TRG_TOPK_MAX_CHUNK(1, 0) }
-        if (CW > 64) tmem_ld_wait();
-        if (CW > 96) tmem_ld_32x32(t_row + 96u, v + 96);
-        if (CW > 64) { TRG_TOPK_MAX_CHUNK(2, 0) }
-        if (CW > 96) {
+        if constexpr (CW > 32) tmem_ld_wait();
+        if constexpr (CW > 64) tmem_ld_32x32(t_row + 64u, v + 64);
+        if constexpr (CW > 32) { TRG_TOPK_MAX_CHUNK(1, 0) }
+        if constexpr (CW > 64) tmem_ld_wait();
+        if constexpr (CW > 96) tmem_ld_32x32(t_row + 96u, v + 96);
+        if constexpr (CW > 64) { TRG_TOPK_MAX_CHUNK(2, 0) }
+        if constexpr (CW > 96) {
           tmem_ld_wait();
           TRG_TOPK_MAX_CHUNK(3, 0)
         }
