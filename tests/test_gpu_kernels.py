@@ -397,6 +397,20 @@ def test_score_topk_bf16_tensor_core_integer_exact(dev, b, p, h, k):
     assert torch.equal(gv.cpu(), vals) and torch.equal(gi.cpu(), ids + 7)
 
 
+def test_score_topk_bf16_large_catalogue(dev):
+    """4.2M posts (tens of thousands of tiles per split, thresholds shared across splits): bit-exact, ties
+    included.  (A pre-warm of the thresholds from the top-K of the first 4096 posts was measured on config 5:
+    exact, but 84.18 vs 84.19 ms -- the cold start of the lists is not what costs time -- and removed.)"""
+    b, p, h, k = 9, (1 << 22) + 12_345, 64, 20
+    g = torch.Generator().manual_seed(99)
+    q = torch.randint(0, 4, (b, h), generator=g).float()
+    cat = torch.randint(0, 3, (p, h), generator=g).float()
+    cat[torch.rand(p, generator=g) < 0.05] = 0
+    vals, ids = otopk.score_topk(q, cat, k)
+    gv, gi = trg.score_topk(q.to(dev).bfloat16(), cat.to(dev).bfloat16(), k, id_offset=3)
+    assert torch.equal(gv.cpu(), vals) and torch.equal(gi.cpu(), ids + 3)
+
+
 def test_score_topk_bf16_random(dev):
     q, cat = synth.synth_queries(200, 100_000, 128, zero_frac=0.05)
     qb, cb = q.bfloat16(), cat.bfloat16()
