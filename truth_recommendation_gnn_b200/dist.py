@@ -202,9 +202,15 @@ def allreduce_grads(params):
     flat = torch.cat([g.reshape(-1).float() for g in grads])
     dist.all_reduce(flat)
     off = 0
-    for g in grads:
+    for p in params:
+        g = p.grad
+        if g is None:
+            continue
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        if g.dtype == torch.float32:
+            p.grad = flat[off:off + n].view_as(g)      # a view of the reduced buffer: no copy-back kernel
+        else:
+            g.copy_(flat[off:off + n].view_as(g))
         off += n
 
 
