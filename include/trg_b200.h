@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TRG_ABI_VERSION 2
+#define TRG_ABI_VERSION 3
 
 enum { TRG_F32 = 0, TRG_BF16 = 1 };
 enum {
@@ -90,20 +90,34 @@ int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const void* x_sr
  * accumulate != 0 adds to the rows already in g_src_out (autograd's gradient accumulation of a table
  * that feeds several relations, fused); relu_of (nullable, [n_src, feat] dtype) is the forward
  * activation the gradient belongs to: rows are finally gated by relu_of > 0, i.e. the ReLU backward
- * of train_gnn.py:187-198 (aten threshold_backward) fused into the last accumulating pass. */
+ * of train_gnn.py:187-198 (aten threshold_backward) fused into the last accumulating pass.
+ * out_dtype = dtype, or TRG_F32 with dtype = TRG_BF16: the sums are written (and accumulated) as fp32
+ * rows -- partial sums that a multi-GPU run reduces across ranks are rounded to bf16 once, after the
+ * cross-rank add (trg_rows_finish), like the single-GPU kernel rounds once after its fp32 accumulation. */
 int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
                      const void* g_mean, int64_t n_src, int32_t feat, int dtype,
-                     void* g_src_out /* [n_src, feat] dtype */, int accumulate, const void* relu_of,
-                     const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
+                     void* g_src_out /* [n_src, feat] out_dtype */, int out_dtype, int accumulate,
+                     const void* relu_of, const trg_long_rows* long_rows /* host struct, nullable */,
+                     void* stream);
 
 /* ---- generic weighted segmented gather-sum (used by the loss backward) ------------------------
  *     out[r] (+)= scale * sum_{j in row r} coef[eid[j]] * x[col[j]]
- * scale is a device scalar (nullable = 1); accumulate != 0 adds to out; relu_of as in
- * trg_sage_agg_bwd (applied after the accumulation). */
+ * scale is a device scalar (nullable = 1); accumulate != 0 adds to out; relu_of and out_dtype as in
+ * trg_sage_agg_bwd (relu_of applied after the accumulation). */
 int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                     const float* coef, const float* scale, const void* x,
-                    int64_t n_rows, int32_t feat, int dtype, void* out, int accumulate,
+                    int64_t n_rows, int32_t feat, int dtype, void* out, int out_dtype, int accumulate,
                     const void* relu_of, const trg_long_rows* long_rows /* host struct, nullable */, void* stream);
+
+/* ---- row-wise finish of a cross-GPU reduced table (multi-GPU only; no single-GPU counterpart) ---
+ *     out[r, :] = gate( row_scale[r] * in[r, :] + add[r, :] )
+ * in: [n_rows, feat] of in_dtype (TRG_F32 for fp32-transported partial sums); row_scale (nullable, fp32
+ * [n_rows]) = 1 / max(global in-degree, 1) of a source-partitioned mean; add (nullable, dtype) = the local
+ * gradient term of the same rows; gate: relu_of (nullable, dtype) > 0 ? value : 0 -- the ReLU backward of
+ * train_gnn.py:187-198.  One pass over 1/G of a table instead of three element-wise torch kernels;
+ * the arithmetic is fp32 and out is rounded to dtype once.  out may alias add. */
+int trg_rows_finish(const void* in, int in_dtype, const float* row_scale, const void* add,
+                    const void* relu_of, int64_t n_rows, int32_t feat, int dtype, void* out, void* stream);
 
 /* ---- A5+A6 / K4: fused positive/negative edge score + BCE-with-logits -------------------------
  * Replaces train_gnn.py:259-281:  pos = <u[pos_u], p[pos_p]>, neg = <u[pos_u], p[neg_p]>,

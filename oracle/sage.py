@@ -63,13 +63,18 @@ class SAGEConvOracle(torch.nn.Module):
 
 
 class WeightedRGCNOracle(torch.nn.Module):
-    """train_gnn.py:147-200 verbatim (one hetero layer, fixed python-float weights)."""
+    """train_gnn.py:147-200 verbatim (one hetero layer, fixed python-float weights).  ``conv_cls`` is the
+    name the reference imports at train_gnn.py:6 (``SAGEConv``): the oracle's restatement by default; the
+    drop-in tests bind the product's ``SAGEConv`` instead -- the import swap INTEGRATION.md describes --
+    while every other line stays stock torch.  Pinned to the reference's own class text by
+    tests/test_oracle.py (``ref_exec_*`` fixtures, tests/golden/make_golden_ref.py)."""
 
-    def __init__(self, hidden_dim=64, in_channels=(-1, -1)):
+    def __init__(self, hidden_dim=64, in_channels=(-1, -1), conv_cls=None):
         super().__init__()
-        self.msg_direct = SAGEConvOracle(in_channels, hidden_dim)   # user <- post
-        self.msg_social = SAGEConvOracle(in_channels, hidden_dim)   # user <- user
-        self.post_update = SAGEConvOracle(in_channels, hidden_dim)  # post <- user
+        conv_cls = conv_cls or SAGEConvOracle
+        self.msg_direct = conv_cls(in_channels, hidden_dim)   # user <- post
+        self.msg_social = conv_cls(in_channels, hidden_dim)   # user <- user
+        self.post_update = conv_cls(in_channels, hidden_dim)  # post <- user
         self.w_direct = 1.0
         self.w_social = 0.75
 
@@ -82,6 +87,26 @@ class WeightedRGCNOracle(torch.nn.Module):
         return {"user": user_out, "post": post_out}
 
 
+def relu_margin(model, x_dict, edge_index_dict) -> float:
+    """Smallest |pre-activation| / max|pre-activation| over every ReLU input of ``model`` (a
+    ``WeightedRGCNOracle`` or a stack of them).  A test input whose margin is above fp32 rounding noise has
+    no ReLU gate that two correct fp32 implementations could decide differently, so gradient parity on it is
+    well posed.  Computed from the ORACLE alone (run it in fp64); it says nothing about the code under test."""
+    layers = list(model.layers) if hasattr(model, "layers") else [model]
+    margin = float("inf")
+    with torch.no_grad():
+        for layer in layers:
+            user_x, post_x = x_dict["user"], x_dict["post"]
+            z_u = (layer.w_direct * layer.msg_direct((post_x, user_x), edge_index_dict[REL_DIRECT])
+                   + layer.w_social * layer.msg_social((user_x, user_x), edge_index_dict[REL_SOCIAL]))
+            z_p = layer.post_update((user_x, post_x), edge_index_dict[REL_ENGAGE])
+            for z in (z_u, z_p):
+                if z.numel():
+                    margin = min(margin, float(z.abs().min() / z.abs().max().clamp(min=1e-30)))
+            x_dict = {"user": F.relu(z_u), "post": F.relu(z_p)}
+    return margin
+
+
 class StackedWeightedRGCNOracle(torch.nn.Module):
     """L stacked ``WeightedRGCN`` blocks (SURVEY.md §8 stacking rule; the reference has L = 1).
 
@@ -89,10 +114,10 @@ class StackedWeightedRGCNOracle(torch.nn.Module):
     layer l-1; ReLU after every layer including the last.
     """
 
-    def __init__(self, hidden_dim=64, num_layers=2, in_channels=(-1, -1)):
+    def __init__(self, hidden_dim=64, num_layers=2, in_channels=(-1, -1), conv_cls=None):
         super().__init__()
         self.layers = torch.nn.ModuleList(
-            [WeightedRGCNOracle(hidden_dim, in_channels if i == 0 else (hidden_dim, hidden_dim))
+            [WeightedRGCNOracle(hidden_dim, in_channels if i == 0 else (hidden_dim, hidden_dim), conv_cls)
              for i in range(num_layers)])
 
     def forward(self, x_dict, edge_index_dict):
@@ -126,7 +151,7 @@ def train_step(model, optimizer, x_dict, edge_index_dict, train_edge_index,
     user_emb, post_emb = out["user"], out["post"]
     pos_u, pos_p = train_edge_index
     if neg_p is None:
-        neg_p = torch.randint(0, num_posts, (pos_p.size(0),))
+        neg_p = torch.randint(0, num_posts, (pos_p.size(0),), device=pos_p.device)
     loss = link_loss(user_emb, post_emb, pos_u, pos_p, neg_p, interaction_type_tensor, num_users)
     loss.backward()
     optimizer.step()

@@ -9,7 +9,7 @@ from oracle import topk as otopk
 
 class OracleOps:
     @staticmethod
-    def gather_sum(rel, which, x):
+    def gather_sum(rel, which, x, out_dtype=None):
         ei = rel.edge_index
         if which == "fwd":
             return torch.zeros(rel.n_dst, x.size(1), dtype=x.dtype).index_add_(0, ei[1], x[ei[0]])
@@ -86,13 +86,24 @@ class OracleStepPrims:
         return mean
 
     @staticmethod
-    def gather_sum(rel, which, x, out=None, accumulate=False, relu_of=None):
+    def gather_sum(rel, which, x, out=None, accumulate=False, relu_of=None, out_dtype=None):
         g = OracleOps.gather_sum(rel, which, x)
         if out is not None and accumulate:
             g = out + g
         if relu_of is not None:
             g = torch.where(relu_of > 0, g, torch.zeros_like(g))
         return g
+
+    @staticmethod
+    def rows_finish(x, dtype, row_scale=None, add=None, relu_of=None):
+        y = x.float()
+        if row_scale is not None:
+            y = y * row_scale[:, None]
+        if add is not None:
+            y = y + add.float()
+        if relu_of is not None:
+            y = torch.where(relu_of > 0, y, torch.zeros_like(y))
+        return y.to(dtype)
 
     @staticmethod
     def proj_fwd(terms, bias, relu):
@@ -120,5 +131,5 @@ class OracleStepPrims:
         return loss, coef, g
 
     @staticmethod
-    def wsum(csr, coef, x, out=None, accumulate=False):
+    def wsum(csr, coef, x, out=None, accumulate=False, out_dtype=None):
         return OracleLossOps.wsum(csr, coef, x, 1.0, out if accumulate else None)

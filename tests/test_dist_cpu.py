@@ -25,6 +25,7 @@ def _worker(rank, world, port, q, fused=False):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
+        torch.manual_seed(1000 + rank)        # the ranks' default generators are unrelated, as in a real launch
         g = synth.synth_graph(U, P, EE, ES, H, seed=0)
         shard = tdist.ShardedGraph(g.x_dict, g.edge_index_dict, g.train_edge_index,
                                    g.interaction_type_tensor, U, P)
@@ -48,10 +49,13 @@ def _worker(rank, world, port, q, fused=False):
         qv, cat = synth.synth_queries(7, P, H, zero_frac=0.2)
         cat_local = cat[shard.p0:shard.p1].contiguous()
         rv, ri = tdist.recommend_sharded(qv, cat_local, 10, shard.p0, oracle_ops.score_topk, oracle_ops.merge)
+        # negatives drawn inside the step (neg_p_global=None) must be ONE array shared by all ranks
+        n1, n2 = shard.draw_negatives(), shard.draw_negatives()
+        assert n1.shape == (EE,) and int(n1.min()) >= 0 and int(n1.max()) < P and not torch.equal(n1, n2)
         # numpy payloads: tensors sent through mp queues need the sender alive until they are read
         q.put((rank, losses, {k: v.detach().numpy().copy() for k, v in model.state_dict().items()},
                out["user"][:shard.u1 - shard.u0].numpy().copy(), out["post"][:shard.p1 - shard.p0].numpy().copy(),
-               rv.numpy().copy(), ri.numpy().copy()))
+               rv.numpy().copy(), ri.numpy().copy(), torch.stack([n1, n2]).numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -67,6 +71,8 @@ def test_sharded_train_step_and_topk_match_single_process(fused):
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
     t = torch.from_numpy
+    negs = [t(r[7]) for r in res]
+    assert all(torch.equal(n, negs[0]) for n in negs), "ranks drew different negatives"
     res = [(r[0], r[1], {k: t(v) for k, v in r[2].items()}, t(r[3]), t(r[4]), t(r[5]), t(r[6])) for r in res]
     for p in procs:
         p.join(timeout=60)

@@ -441,3 +441,72 @@ def test_score_topk_float_and_sharded(dev):
     parts = [trg.score_topk(q.to(dev), cat[a:b].to(dev).contiguous(), 10, id_offset=a) for a, b in bounds]
     mv, mi = trg.topk_merge(torch.cat([x[0] for x in parts], 1), torch.cat([x[1] for x in parts], 1), 3, 10)
     assert torch.equal(mv, gv) and torch.equal(mi, gi)
+
+
+# ------------------------------------------------------------- fp32 sum rows / row finish (multi-GPU path)
+@pytest.mark.parametrize("f,long_rows", [(128, False), (256, False), (64, False), (16, False), (128, True)])
+def test_gather_fp32_output_rows_for_bf16_tables(dev, f, long_rows, monkeypatch):
+    """out_dtype = fp32 with a bf16 table (the partial sums a multi-GPU run reduces across ranks): the rows
+    are the UNROUNDED fp32 accumulations -- 1e-5 against an fp64 sum of the bf16 inputs, where the bf16
+    output would only be good to 4e-3 -- including accumulate and the long-row combine."""
+    if long_rows:
+        from truth_recommendation_gnn_b200 import graph as G
+        monkeypatch.setattr(G, "LONG_ROW_THRESHOLD", 64)
+    x, ei = _agg_case(300, 200, 6000, f, 5 + f, skew=True)
+    xb = x.bfloat16()
+    gen = torch.Generator().manual_seed(3)
+    coef = torch.randn(6000, generator=gen)
+    csr = trg.RelationGraph(ei.to(dev), 300, 200).fwd
+    s_plain = torch.zeros(200, f, dtype=torch.float64).index_add_(0, ei[1], xb.double()[ei[0]])
+    s_coef = torch.zeros(200, f, dtype=torch.float64).index_add_(0, ei[1], coef.double()[:, None] * xb.double()[ei[0]])
+    out = Fn.sage_agg_bwd(csr, None, xb.to(dev), out_dtype=torch.float32)
+    assert out.dtype == torch.float32
+    assert_close(out.cpu(), s_plain, TOL_F32, "fp32 sum rows of a bf16 table")
+    Fn.gather_wsum(csr, coef.to(dev), xb.to(dev), out=out, accumulate=True)           # accumulates in fp32
+    assert_close(out.cpu(), s_plain + s_coef, TOL_F32, "fp32 rows, accumulate")
+    rounded = Fn.sage_agg_bwd(csr, None, xb.to(dev))
+    assert rounded.dtype == torch.bfloat16
+    assert_close(rounded.float().cpu(), s_plain, TOL_BF16, "bf16 rows")
+    with pytest.raises(trg._lib.TrgError):
+        Fn.sage_agg_bwd(csr, None, x.to(dev), out_dtype=torch.bfloat16)               # only bf16 -> fp32 exists
+
+
+@pytest.mark.parametrize("dtype,in_f32", [(torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)])
+def test_rows_finish(dev, dtype, in_f32):
+    """trg_rows_finish: out = gate(row_scale * in + add), fp32 arithmetic, one rounding."""
+    gen = torch.Generator().manual_seed(1)
+    n, f = 1000, 128
+    x = torch.randn(n, f, generator=gen)
+    x = x if in_f32 else x.bfloat16().float()
+    add = torch.randn(n, f, generator=gen).to(dtype).float()
+    act = torch.relu(torch.randn(n, f, generator=gen)).to(dtype).float()
+    rs = torch.rand(n, generator=gen)
+    xd = x.to(dev) if in_f32 else x.to(dev).to(dtype)
+    tol = TOL_F32 if dtype == torch.float32 else 2.0 ** -8          # one bf16 rounding of the result
+    out = Fn.rows_finish(xd, dtype, row_scale=rs.to(dev))
+    assert out.dtype == dtype
+    assert_close(out.float().cpu(), x.double() * rs.double()[:, None], tol, "row scale")
+    out = Fn.rows_finish(xd, dtype, add=add.to(dev).to(dtype), relu_of=act.to(dev).to(dtype))
+    exp = torch.where(act > 0, x.double() + add.double(), torch.zeros((), dtype=torch.float64))
+    assert_close(out.float().cpu(), exp, tol, "add + gate")
+    assert bool((out.float().cpu()[act <= 0] == 0).all())
+    if dtype == torch.float32:
+        assert torch.equal(out.cpu(), torch.where(act > 0, x + add, torch.zeros(())))    # exactly torch's fp32
+    assert Fn.rows_finish(xd[:0], dtype).shape == (0, f)
+
+
+def test_csr_build_aborts_on_out_of_range_per_step_ids(dev):
+    """Per-step structures skip the host-side range check (no sync inside a step); K0's histogram pass then
+    aborts the kernel on an id outside [0, n_key) instead of corrupting memory.  The abort poisons the CUDA
+    context, so it is observed in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch, truth_recommendation_gnn_b200 as trg\n"
+            "k = torch.tensor([0, 7, 2], device='cuda'); o = torch.tensor([0, 1, 1], device='cuda')\n"
+            "trg.build_csr(o, k, 3, 2, validate=False, per_step=True)\n"
+            "torch.cuda.synchronize()\nprint('NOT DETECTED')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode != 0 and "NOT DETECTED" not in r.stdout, r.stdout + r.stderr
+    assert "outside [0, 3)" in r.stdout + r.stderr

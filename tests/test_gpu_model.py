@@ -6,10 +6,18 @@ import torch
 import truth_recommendation_gnn_b200 as trg
 from oracle import sage as osage
 from oracle import topk as otopk
-from tests.util import TOL_BF16, TOL_F32, assert_close, golden_graph, load_golden, oracle_model
+from tests.util import (TOL_BF16, TOL_F32, assert_as_accurate_as_fp32, assert_close, assert_close_elementwise,
+                        golden_graph, load_golden, oracle_model)
 from truth_recommendation_gnn_b200 import synth
 
 pytestmark = pytest.mark.gpu
+
+
+def _fp64_forward(h, layers, sd, g):
+    """The oracle run in fp64 on the same inputs: the yardstick for tensors with cancellation."""
+    m64 = oracle_model(h, layers, sd).double()
+    with torch.no_grad():
+        return m64({k: v.double() for k, v in g.x_dict.items()}, g.edge_index_dict)
 
 
 def _gpu_model(h, layers, sd, dev, dtype=torch.float32):
@@ -66,8 +74,9 @@ def test_golden_forward_train_topk(dev, name):
     model = _gpu_model(m["h"], m["layers"], fix["state_dict"], dev)
     with torch.no_grad():
         out = model(g.x_dict, g.edge_index_dict)
-    assert_close(out["user"].cpu(), fix["out0_user"], TOL_F32, "user emb")
-    assert_close(out["post"].cpu(), fix["out0_post"], TOL_F32, "post emb")
+    o64 = _fp64_forward(m["h"], m["layers"], fix["state_dict"], golden_graph(fix))
+    assert_as_accurate_as_fp32(out["user"].cpu(), fix["out0_user"], o64["user"], TOL_F32, "user emb")
+    assert_as_accurate_as_fp32(out["post"].cpu(), fix["out0_post"], o64["post"], TOL_F32, "post emb")
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     for s in range(m["steps"]):
         loss = trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
@@ -80,7 +89,7 @@ def test_golden_forward_train_topk(dev, name):
         out1 = model(g.x_dict, g.edge_index_dict)
     assert_close(out1["user"].cpu(), fix["out1_user"], 5 * TOL_F32, "user emb after training")
     gv, gi = trg.recommend(out1["user"], out1["post"], k=m["k"])
-    assert_close(gv.cpu(), fix["topk_vals"], 5 * TOL_F32, "top-k scores")
+    assert_close_elementwise(gv.cpu(), fix["topk_vals"], 5 * TOL_F32, "top-k scores")
     # ids must agree wherever the oracle's ranking is not a near-tie
     sc = fix["out1_user"] @ fix["out1_post"].t()
     srt = torch.sort(sc, dim=1, descending=True)[0][:, :m["k"] + 1]
@@ -169,24 +178,25 @@ def test_fused_step_matches_autograd_and_oracle(dev, layers, h, dtype, tol):
     sd = synth.init_state_dict(h, h, layers)
     rnd = (lambda t: t.to(dtype).float())
     neg = synth.synth_neg(P, Ee, 2)
-    # ReLU is discontinuous: an element whose pre-activation is within rounding of 0 can be gated
-    # differently by two correct fp32 implementations, which moves the gradients by far more than
-    # 1e-5.  Use the first seeded graph on which every layer's gates agree with the oracle's.
+    # ReLU is discontinuous: a pre-activation within rounding of 0 can be gated either way by two correct fp32
+    # implementations.  The test input is chosen by a property of the ORACLE alone (fp64 run): the first seeded
+    # graph whose smallest |pre-activation| is > 1e-6 of the layer's scale -- nothing about the code under test
+    # enters the choice.
     for seed in range(11, 19):
         g = synth.synth_graph(U, P, Ee, Es, h, seed=seed, skew=True)
-        ref = oracle_model(h, layers, {k: rnd(v) for k, v in sd.items()})
         xr = {k: rnd(v) for k, v in g.x_dict.items()}
-        gd = g.to(dev)
-        xd = {k: v.to(dtype) for k, v in gd.x_dict.items()}
-        probe = _gpu_model(h, layers, sd, dev, dtype)
-        mism, a, b = 0, xr, xd
-        with torch.no_grad():
-            for lr_, lg_ in zip(ref.layers if layers > 1 else [ref], probe.layers if layers > 1 else [probe]):
-                a, b = lr_(a, g.edge_index_dict), lg_(b, gd.edge_index_dict)
-                mism += sum(int(((a[k] > 0) != (b[k].float().cpu() > 0)).sum()) for k in ("user", "post"))
-        if mism == 0 or dtype != torch.float32:      # bf16: flips are inside the 1e-2 band anyway
+        m64 = oracle_model(h, layers, {k: rnd(v) for k, v in sd.items()}).double()
+        x64 = {k: v.double() for k, v in xr.items()}
+        if osage.relu_margin(m64, x64, g.edge_index_dict) > 1e-6:
             break
-    assert mism == 0 or dtype != torch.float32, "no seed without a ReLU gate flip"
+    else:
+        raise AssertionError("no seeded graph with a ReLU margin above fp32 rounding")
+    ref = oracle_model(h, layers, {k: rnd(v) for k, v in sd.items()})
+    gd = g.to(dev)
+    xd = {k: v.to(dtype) for k, v in gd.x_dict.items()}
+    o64 = m64(x64, g.edge_index_dict)
+    osage.link_loss(o64["user"], o64["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
+                    g.interaction_type_tensor.double(), U).backward()
     out = ref(xr, g.edge_index_dict)
     l_ref = osage.link_loss(out["user"], out["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
                             g.interaction_type_tensor, U)
@@ -204,9 +214,13 @@ def test_fused_step_matches_autograd_and_oracle(dev, layers, h, dtype, tol):
     for (n, a), (_, b), (_, r) in zip(m_fused.named_parameters(), m_auto.named_parameters(), ref.named_parameters()):
         assert a.grad is not None and a.grad.dtype == a.dtype, n
         assert_close(a.grad.float().cpu(), b.grad.float().cpu(), tol, f"fused vs autograd grad {n}")
-        # bf16 stores every intermediate gradient table in bf16 and flips ReLU gates near 0: deeper
-        # layers are only checked against the tape path (same storage), the last layer against the oracle
-        if dtype == torch.float32 or layers == 1 or n.startswith(f"layers.{layers - 1}."):
+        g64 = dict(m64.named_parameters())[n].grad
+        if dtype == torch.float32:
+            # as close to the fp64 oracle as the reference's own fp32 arithmetic (the fp32 CPU oracle) is
+            assert_as_accurate_as_fp32(a.grad.cpu(), r.grad, g64, tol, f"fused vs oracle grad {n}")
+        elif layers == 1 or n.startswith(f"layers.{layers - 1}."):
+            # bf16 stores every intermediate gradient table in bf16 and flips ReLU gates near 0: deeper
+            # layers are only checked against the tape path (same storage), the last layer against the oracle
             assert_close(a.grad.float().cpu(), r.grad, tol, f"fused vs oracle grad {n}")
     # a second call accumulates like loss.backward() does
     g0 = {n: p.grad.clone() for n, p in m_fused.named_parameters()}
@@ -304,3 +318,122 @@ def test_csr_cache_round_trip_skips_k0(dev, tmp_path):
         model(g.x_dict, g.edge_index_dict)
     assert n1 - n0 == _lib.launch_count() - n1               # first forward after load == steady state: no K0
     assert torch.equal(out2["user"], out["user"].detach()) and torch.equal(out2["post"], out["post"].detach())
+
+
+def _ref_exec_graph(m):
+    return synth.synth_graph(m["u"], m["p"], m["e_eng"], m["e_soc"], m["h"], seed=0, skew=m["skew"])
+
+
+def _ref_exec_negatives(m):
+    """The negatives the reference's train() drew (train_gnn.py:272) when the fixture was generated:
+    ``torch.manual_seed(seed)`` then one ``torch.randint(0, num_posts, (E,))`` per step."""
+    torch.manual_seed(m["seed"])
+    return [torch.randint(0, m["p"], (m["e_eng"],)) for _ in range(m["steps"])]
+
+
+@pytest.mark.parametrize("name", ["ref_exec_small", "ref_exec_skew"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_against_reference_executed_fixture(dev, name, fused):
+    """The product against outputs of the REFERENCE'S OWN ``WeightedRGCN`` / ``train()`` / ``evaluate()``
+    source (tests/golden/make_golden_ref.py executed it in the build container; only ``SAGEConv`` was bound
+    to the oracle's): embeddings, the loss of every step, the last step's gradients, weights after Adam,
+    Recall@10 / NDCG@10."""
+    fix = load_golden(name)
+    m = fix["meta"]
+    g = _ref_exec_graph(m)
+    gd = g.to(dev)
+    model = _gpu_model(m["h"], 1, fix["state_dict"], dev)
+    o64 = _fp64_forward(m["h"], 1, fix["state_dict"], g)
+    with torch.no_grad():
+        out = model(gd.x_dict, gd.edge_index_dict)
+    assert_as_accurate_as_fp32(out["user"].cpu(), fix["out0_user"], o64["user"], TOL_F32, "user emb vs reference run")
+    assert_as_accurate_as_fp32(out["post"].cpu(), fix["out0_post"], o64["post"], TOL_F32, "post emb vs reference run")
+    opt = torch.optim.Adam(model.parameters(), lr=0.001)
+    for s, neg in enumerate(_ref_exec_negatives(m)):
+        loss = trg.train_step(model, opt, gd.x_dict, gd.edge_index_dict, gd.train_edge_index,
+                              gd.interaction_type_tensor, m["u"], m["p"], neg_p=neg.to(dev), fused=fused)
+        ref = float(fix["losses"][s])
+        assert abs(loss - ref) <= TOL_F32 * abs(ref), (s, loss, ref)
+    for n, p in model.named_parameters():
+        assert_close(p.grad.cpu(), fix["last_grads"][n], 5 * TOL_F32, f"grad {n} vs reference run")
+        # Adam moves a weight by ~lr per step whatever the gradient's size (a gradient entry near its eps is
+        # normalised to a fraction of lr that rounding noise can change): compare at that scale
+        assert float((p.detach().cpu() - fix["state_dict_after"][n]).abs().max()) <= 0.25 * 0.001 * m["steps"], n
+    with torch.no_grad():
+        out1 = model(gd.x_dict, gd.edge_index_dict)
+    rec, ndcg = trg.evaluate(fix["test_edges"].to(dev), out1["user"], out1["post"], K=m["k"], num_users=m["u"])
+    # the reference's evaluate() ran on ITS post-training embeddings; ours differ by ~1e-5, which can swap
+    # near-tied ranks of a few users: metrics agree to 1 / (number of test users)
+    n_users = int(torch.unique(fix["test_edges"][0]).numel())
+    assert abs(rec - fix["recall"]) <= 2.0 / n_users and abs(ndcg - fix["ndcg"]) <= 2.0 / n_users, (rec, ndcg)
+    # and exactly, when fed the reference run's own embeddings
+    rec2, ndcg2 = trg.evaluate(fix["test_edges"].to(dev), fix["out1_user"].to(dev), fix["out1_post"].to(dev),
+                               K=m["k"], num_users=m["u"])
+    assert abs(rec2 - fix["recall"]) < 1e-9 and abs(ndcg2 - fix["ndcg"]) < 1e-6, (rec2, ndcg2)
+
+
+@pytest.mark.parametrize("name", ["ref_exec_small", "ref_exec_skew"])
+def test_import_swap_only(dev, name):
+    """INTEGRATION.md §1, literally: the reference's model class and train() body with ONLY the name
+    ``SAGEConv`` rebound to the product's (``oracle.sage.WeightedRGCNOracle`` / ``train_step`` are the
+    restatements of train_gnn.py:147-200,242-285 that tests/test_oracle.py pins to the reference's text; the
+    reference source itself cannot travel to the GPU box).  Every other line -- relation combine, ReLU,
+    ``user_emb[pos_u] * post_emb[pos_p]``, BCEWithLogitsLoss, ``loss.backward()``, Adam -- is stock torch on
+    CUDA, as it would be for a maintainer who swaps the import and nothing else."""
+    from truth_recommendation_gnn_b200 import _lib
+    fix = load_golden(name)
+    m = fix["meta"]
+    gd = _ref_exec_graph(m).to(dev)
+    model = osage.WeightedRGCNOracle(hidden_dim=m["h"], conv_cls=trg.SAGEConv)     # SAGEConv((-1, -1), hidden)
+    opt_early = torch.optim.Adam(model.parameters(), lr=0.001)                     # train_gnn.py:206-207 order
+    model.load_state_dict(fix["state_dict"])
+    model = model.to(dev)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        out = model(gd.x_dict, gd.edge_index_dict)
+    assert _lib.launch_count() - n0 >= 6            # 3 aggregations + 3 fused projections: nothing on cuBLAS
+    assert_close(out["user"].cpu(), fix["out0_user"], TOL_F32, "user emb, import swap")
+    assert_close(out["post"].cpu(), fix["out0_post"], TOL_F32, "post emb, import swap")
+    opt = torch.optim.Adam(model.parameters(), lr=0.001)
+    for s, neg in enumerate(_ref_exec_negatives(m)):
+        loss = osage.train_step(model, opt, gd.x_dict, gd.edge_index_dict, gd.train_edge_index,
+                                gd.interaction_type_tensor, m["u"], m["p"], neg_p=neg.to(dev))
+        ref = float(fix["losses"][s])
+        assert abs(loss - ref) <= TOL_F32 * abs(ref), (s, loss, ref)
+    for n, p in model.named_parameters():
+        assert_close(p.grad.cpu(), fix["last_grads"][n], 5 * TOL_F32, f"grad {n}, import swap")
+    del opt_early
+
+
+def test_cfg1_full_size_against_oracle(dev):
+    """BASELINE config 1 at FULL size (10k users / 50k posts / 500k edges, H = 64): the literal L = 1 model
+    and the L = 2 stack, forward + one train step + top-10, against the CPU oracle (fp32) judged by the fp64
+    oracle."""
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    U, P, Ee, Es, H = 10_000, 50_000, 400_000, 100_000, 64
+    g = synth.synth_graph(U, P, Ee, Es, H, seed=0)
+    gd = g.to(dev)
+    neg = synth.synth_neg(P, Ee, 0)
+    for L in (1, 2):
+        sd = synth.init_state_dict(H, H, L)
+        ref = oracle_model(H, L, sd)
+        model = _gpu_model(H, L, sd, dev)
+        o64 = _fp64_forward(H, L, sd, g)
+        with torch.no_grad():
+            exp = ref(g.x_dict, g.edge_index_dict)
+            out = model(gd.x_dict, gd.edge_index_dict)
+        for k in ("user", "post"):
+            assert_as_accurate_as_fp32(out[k].cpu(), exp[k], o64[k], TOL_F32, f"cfg1 L={L} {k} emb")
+        ev, ei = otopk.score_topk(exp["user"][:512], exp["post"], 10)
+        gv, gi = trg.recommend(out["user"][:512], out["post"], k=10)
+        assert_close_elementwise(gv.cpu(), ev, TOL_F32, f"cfg1 L={L} top-10 scores")
+        gap = ev[:, :-1] - ev[:, 1:]
+        clear = (gap > 1e-4 * ev[:, :1].abs().clamp(min=1e-6)).all(dim=1)        # rows without a near-tie
+        assert clear.float().mean() > 0.5 and torch.equal(gi.cpu()[clear], ei[clear])
+        l_ref = osage.train_step(ref, torch.optim.Adam(ref.parameters(), lr=1e-3), g.x_dict, g.edge_index_dict,
+                                 g.train_edge_index, g.interaction_type_tensor, U, P, neg_p=neg)
+        l_gpu = trg.train_step(model, torch.optim.Adam(model.parameters(), lr=1e-3), gd.x_dict, gd.edge_index_dict,
+                               gd.train_edge_index, gd.interaction_type_tensor, U, P, neg_p=neg.to(dev))
+        assert abs(l_gpu - l_ref) <= TOL_F32 * abs(l_ref), (L, l_gpu, l_ref)
+        for (n, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
+            assert_close(a.grad.cpu(), b.grad, 5 * TOL_F32, f"cfg1 L={L} grad {n}")

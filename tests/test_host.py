@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/trg_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "python binding and header disagree"
-    assert _lib.load().trg_abi_version() == 2
+    assert _lib.load().trg_abi_version() == _lib.ABI_VERSION
     assert _lib.load().trg_csr_workspace_bytes(1000, 100) > 4 * 4 * 1000
 
 
@@ -119,6 +119,38 @@ def test_vectorised_graph_prep_matches_reference_loops():
     assert torch.equal(e, e_ref) and torch.equal(a, a_ref) and e.dtype == torch.int64
     train = df[df["post_id"] < 100].sort_values("timestamp").reset_index(drop=True)
     assert torch.equal(graph_io.interaction_type_table(train, post_to_idx), oprep.interaction_type_table(train, post_to_idx))
+
+
+def test_temporal_split_and_degree_features_match_reference_loops():
+    """§8f N4 remainder: chronological 80/10/10 split (train_gnn.py:28-35) and the per-user degree /
+    engagement features (build_graph.py:409-429) against their literal loops."""
+    import numpy as np
+    import pandas as pd
+    from oracle import graph_prep as oprep
+    from truth_recommendation_gnn_b200 import graph_io
+    rng = np.random.default_rng(1)
+    users = [f"u{i}" for i in range(50)]
+    n = 777
+    act = pd.DataFrame({"engager": rng.choice(users + ["ghost"], n), "post_id": rng.integers(0, 90, n),
+                        "timestamp": rng.integers(0, 300, n)})            # many equal timestamps
+    tr, va, te = graph_io.temporal_split(act)
+    tr_r, va_r, te_r = oprep.temporal_split(act)
+    for a, b in ((tr, tr_r), (va, va_r), (te, te_r)):
+        assert a.equals(b)
+    assert len(tr) == int(0.8 * n) and len(tr) + len(va) + len(te) == n
+    u2i = {u: i for i, u in enumerate(users)}
+    soc = pd.DataFrame({"follower": rng.integers(0, 50, 600), "followee": rng.integers(0, 50, 600)})
+    f = graph_io.user_structural_features(soc, act, u2i, 50)
+    assert torch.equal(f, oprep.user_structural_features(soc, act, u2i, 50)) and f.dtype == torch.float32
+
+
+def test_csr_cache_checksum_is_order_sensitive():
+    from truth_recommendation_gnn_b200 import graph_io
+    ei = torch.tensor([[0, 1, 2, 3], [3, 2, 1, 0]])
+    assert graph_io._edge_checksum(ei) != graph_io._edge_checksum(ei.flip(1))
+    assert graph_io._edge_checksum(ei) != graph_io._edge_checksum(ei.flip(0))
+    assert graph_io._edge_checksum(ei) == graph_io._edge_checksum(ei.clone())
+    assert graph_io._edge_checksum(torch.empty(2, 0, dtype=torch.long)) == 0
 
 
 def test_hetero_inputs_follow_train_gnn_assembly():

@@ -35,6 +35,8 @@ class AllGatherRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_full):
+        if g_full.dtype == torch.bfloat16:      # cross-rank add in fp32, one rounding at the owner
+            return reduce_scatter_rows_raw(g_full.float()).to(g_full.dtype)
         return reduce_scatter_rows_raw(g_full)
 
 
@@ -54,10 +56,13 @@ class PushMeanAggFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_local, prel, gather_sum, grad_prescaled):
-        part = gather_sum(prel.rel, "fwd", x_local)                # [n_dst_pad, F]
+        # bf16 tables: fp32 partial sums cross NVLink and the mean is rounded once, at the owner (like the
+        # single-GPU kernel: fp32 accumulate, one rounding)
+        xfer = torch.float32 if x_local.dtype == torch.bfloat16 else None
+        part = gather_sum(prel.rel, "fwd", x_local, xfer)          # [n_dst_pad, F]
         local = reduce_scatter_rows_raw(part)                      # owned destination rows
         ctx.prel, ctx.gather_sum, ctx.grad_prescaled = prel, gather_sum, grad_prescaled
-        return local * prel.inv_deg.to(local.dtype)[:, None]
+        return (local * prel.inv_deg.to(local.dtype)[:, None]).to(x_local.dtype)
 
     @staticmethod
     def backward(ctx, g_mean):

@@ -37,14 +37,28 @@ int proj_simt_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_te
                          int64_t n_rows, int hidden, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace tc
 
-static bool force_simt() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TRG_PROJ_FORCE_SIMT");
-    v = (e && e[0] == '1') ? 1 : 0;
+int grid_sms() {
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  int v = tracked ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+    v = v < kNumSMs ? v : kNumSMs;
+    if (tracked) cache[dev].store(v, std::memory_order_relaxed);
   }
-  return v == 1;
+  return v;
 }
+
+#ifdef TRG_DEBUG
+int debug_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#endif
+
+static bool force_simt() { return debug_env_int("TRG_PROJ_FORCE_SIMT", 0) == 1; }
 
 }  // namespace trg
 

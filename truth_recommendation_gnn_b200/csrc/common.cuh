@@ -11,7 +11,38 @@
 
 namespace trg {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs (persistent grids / workspaces are sized for at most this many CTAs)
+constexpr int kMaxDevices = 64;
+
+// SM count of the CURRENT device (cached per device ordinal), capped at kNumSMs: persistent kernels
+// launch one CTA per SM and their per-CTA workspaces are sized for kNumSMs.
+int grid_sms();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: the "already raised" state is kept
+// per device ordinal (a process may drive several GPUs through this ABI) in atomics (host threads may race;
+// setting the same value twice is harmless).
+struct SmemAttrState {
+  std::atomic<int> bytes[kMaxDevices];
+};
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes, SmemAttrState& st) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && st.bytes[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && tracked) st.bytes[dev].store(bytes, std::memory_order_release);
+  return e;
+}
+
+// A/B and ablation switches exist only in -DTRG_DEBUG builds; the product library never reads the
+// environment on a call path.
+#ifdef TRG_DEBUG
+int debug_env_int(const char* name, int dflt);
+#else
+inline int debug_env_int(const char*, int dflt) { return dflt; }
+#endif
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;

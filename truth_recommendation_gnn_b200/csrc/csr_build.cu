@@ -6,6 +6,7 @@
 // build_graph.py:387,394,402 and train_gnn.py:128-142 (reference keeps COO and scatters with
 // atomics; a stable sort once per static graph makes every later pass atomic-free).
 #include <algorithm>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -108,11 +109,23 @@ int exclusive_scan(const int* in, int* out, int64_t n, int* tile_sums, cudaStrea
 // ---------------------------------------------------------------------------------------------
 // degree histogram
 // ---------------------------------------------------------------------------------------------
+// An id outside [0, n_key) would be an out-of-bounds atomic here and an out-of-bounds row read in every
+// kernel that later follows the CSR: abort the kernel instead (the reference raises IndexError on the CPU and
+// torch's CUDA index kernels raise a device-side assert; this is the same loud failure, not silent
+// corruption).  Static graphs are validated on the host at cache-fill time; this guard covers the per-step
+// structures built from caller-supplied negatives (train_gnn.py:272).
 __global__ void __launch_bounds__(kThreads) count_keys(const long long* __restrict__ key, int64_t n,
-                                                       int* __restrict__ deg) {
+                                                       long long n_key, int* __restrict__ deg) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) atomicAdd(&deg[(int)ldg_stream(key + i)], 1);
+  for (; i < n; i += stride) {
+    const long long k = ldg_stream(key + i);
+    if ((unsigned long long)k >= (unsigned long long)n_key) {
+      printf("trg_csr_build: key %lld at edge %lld is outside [0, %lld)\n", k, (long long)i, n_key);
+      __trap();
+    }
+    atomicAdd(&deg[(int)k], 1);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,7 +300,7 @@ extern "C" int trg_csr_build(const int64_t* other, const int64_t* key, int64_t e
   // degrees -> rowptr (exclusive scan over n_key + 1 entries; entry n_key is 0 -> rowptr[n_key] = E)
   {
     int grid = (int)std::min<int64_t>(ceil_div<int64_t>(e, kThreads), (int64_t)kNumSMs * 16);
-    count_keys<<<grid, kThreads, 0, st>>>((const long long*)key, e, rowptr);
+    count_keys<<<grid, kThreads, 0, st>>>((const long long*)key, e, (long long)n_key, rowptr);
     count_launch();
     TRG_LAUNCH_OK();
     int rc = exclusive_scan(rowptr, rowptr, n_key + 1, w.tile_sums, st);

@@ -536,14 +536,8 @@ int launch_bce(BceArgs& a, int64_t* n_blocks_out, cudaStream_t st, bool dry) {
 
 using namespace trg;
 
-static bool anchor_ring_off() {      // A/B switch: TRG_K4_RING=0 keeps the register form
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TRG_K4_RING");
-    v = (e && e[0] == '0') ? 1 : 0;
-  }
-  return v == 1;
-}
+// A/B switch (TRG_DEBUG builds only): TRG_K4_RING=0 keeps the register form
+static bool anchor_ring_off() { return debug_env_int("TRG_K4_RING", 1) == 0; }
 
 extern "C" size_t trg_edge_bce_workspace_bytes(int64_t n_users) {
   if (n_users < 0) return 0;
@@ -630,16 +624,14 @@ extern "C" int trg_edge_anchor_loss(const int32_t* rowptr, const int32_t* col, c
   int64_t n_blocks = 0;
   if (n_rows > 0 && a.row_vecs == 32 && !anchor_ring_off()) {      // 512-byte rows: cp.async ring form
     n_blocks = ceil_div<int64_t>(n_rows, (int64_t)(kThreads / 32) * 4);
-    static bool attr_set = false;
-    if (!attr_set) {
-      TRG_CUDA(cudaFuncSetAttribute(edge_anchor_ring<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
-      TRG_CUDA(cudaFuncSetAttribute(edge_anchor_ring<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
-      attr_set = true;
-    }
-    if (dtype == TRG_F32)
+    static SmemAttrState attr_f32, attr_bf16;
+    if (dtype == TRG_F32) {
+      TRG_CUDA(ensure_dyn_smem(edge_anchor_ring<float>, kRingBytes, attr_f32));
       edge_anchor_ring<float><<<(unsigned)n_blocks, kThreads, kRingBytes, st>>>(a);
-    else
+    } else {
+      TRG_CUDA(ensure_dyn_smem(edge_anchor_ring<__nv_bfloat16>, kRingBytes, attr_bf16));
       edge_anchor_ring<__nv_bfloat16><<<(unsigned)n_blocks, kThreads, kRingBytes, st>>>(a);
+    }
     count_launch();
     TRG_LAUNCH_OK();
   } else if (n_rows > 0) {

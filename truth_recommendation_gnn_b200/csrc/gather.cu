@@ -13,6 +13,8 @@
 // read coalesced (one per lane) and broadcast by shuffle.  Neighbours are added in CSR order,
 // which is edge order inside a row (stable sort), so fp32 sums equal the CPU scatter_add_ bit
 // for bit.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace trg {
@@ -47,9 +49,39 @@ struct GatherArgs {
   int64_t n_long;
 };
 
-template <typename T, int LPR, int VPL, int MODE>
+// fp32 output rows for a table stored in T (OUTF32; non-mean modes): partial sums that are reduced across
+// GPUs travel in fp32 so that a bf16 model rounds once, after the cross-rank add.  Lane-local layout: the
+// kVec elements a lane holds land at byte offset (lane offset in the T row) * 4 / sizeof(T).
+template <int N>
+__device__ __forceinline__ void load_f32_plain(const char* p, float* f) {
+#pragma unroll
+  for (int k = 0; k < N; k += (N >= 4 ? 4 : 2)) {
+    if (N >= 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p + k * 4);
+      f[k] = v.x; f[k + 1] = v.y; f[k + 2] = v.z; f[k + 3] = v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(p + k * 4);
+      f[k] = v.x; f[k + 1] = v.y;
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_f32_stream(char* p, const float* f) {
+#pragma unroll
+  for (int k = 0; k < N; k += (N >= 4 ? 4 : 2)) {
+    if (N >= 4)
+      stg_stream(p + k * 4, make_uint4(__float_as_uint(f[k]), __float_as_uint(f[k + 1]), __float_as_uint(f[k + 2]),
+                                       __float_as_uint(f[k + 3])));
+    else
+      asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p + k * 4), "r"(__float_as_uint(f[k])),
+                   "r"(__float_as_uint(f[k + 1])) : "memory");
+  }
+}
+
+template <typename T, int LPR, int VPL, int MODE, bool OUTF32 = false>
 __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
   constexpr int kVec = Elem<T>::kVec;
+  constexpr int kOutMul = OUTF32 ? 4 / (int)sizeof(T) : 1;   // output bytes per input byte
   constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
   const int lane = threadIdx.x & 31;
   const int gl = lane & (LPR - 1);
@@ -133,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
   } else if (a.scale) {
     post = __ldg(a.scale);
   }
-  char* ob = reinterpret_cast<char*>(a.out) + (size_t)row * row_bytes + (size_t)gl * 16;
+  char* ob = reinterpret_cast<char*>(a.out) + ((size_t)row * row_bytes + (size_t)gl * 16) * kOutMul;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     if (!act[i]) continue;
@@ -142,7 +174,8 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
       for (int k = 0; k < kVec; ++k) acc[i][k] *= post;
       if (a.accumulate) {
         float f[kVec];
-        Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)i * LPR * 16), f);
+        if (OUTF32) load_f32_plain<kVec>(ob + (size_t)i * LPR * 16 * kOutMul, f);
+        else Elem<T>::unpack(*reinterpret_cast<const uint4*>(ob + (size_t)i * LPR * 16), f);
 #pragma unroll
         for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
       }
@@ -154,7 +187,8 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
         for (int k = 0; k < kVec; ++k) acc[i][k] = f[k] > 0.f ? acc[i][k] : 0.f;
       }
     }
-    stg_stream(ob + (size_t)i * LPR * 16, Elem<T>::pack(acc[i]));
+    if (OUTF32) store_f32_stream<kVec>(ob + (size_t)i * LPR * 16 * kOutMul, acc[i]);
+    else stg_stream(ob + (size_t)i * LPR * 16, Elem<T>::pack(acc[i]));
   }
 }
 
@@ -163,10 +197,11 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
 // are prefetched while the current chunk's rows are in flight, and the running sum is flushed at
 // row boundaries.  Removes the per-row rowptr -> col -> row dependency chain that made short rows
 // (in-degree ~8) latency-bound (profiles/README.md, r1_v1).  Same CSR-order adds: still bit-exact.
-template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT, int VB = 16>
+template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT, int VB = 16, bool OUTF32 = false>
 __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(const GatherArgs a) {
   using V = Vec<T, VB>;
   constexpr int kVec = V::kVec;
+  constexpr int kOutMul = OUTF32 ? 4 / (int)sizeof(T) : 1;
   constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
   static_assert(R < LPR, "row boundaries are held one per lane");
   const int lane = threadIdx.x & 31;
@@ -217,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
       }
       orow = info;
     }
-    char* ob = reinterpret_cast<char*>(a.out) + (size_t)orow * row_bytes + (size_t)gl * VB;
+    char* ob = reinterpret_cast<char*>(a.out) + ((size_t)orow * row_bytes + (size_t)gl * VB) * kOutMul;
     if (MODE == kMean) {
       const float cntf = (float)max(cur_end - cur_beg, 1);
       if (gl == 0 && a.inv_deg_out) a.inv_deg_out[orow] = __fdiv_rn(1.f, cntf);
@@ -234,7 +269,8 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
           for (int k = 0; k < kVec; ++k) acc[i][k] *= post;
           if (a.accumulate) {
             float f[kVec];
-            V::unpack(V::load_plain(ob + (size_t)i * LPR * VB), f);
+            if (OUTF32) load_f32_plain<kVec>(ob + (size_t)i * LPR * VB * kOutMul, f);
+            else V::unpack(V::load_plain(ob + (size_t)i * LPR * VB), f);
 #pragma unroll
             for (int k = 0; k < kVec; ++k) acc[i][k] += f[k];
           }
@@ -246,7 +282,8 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
             for (int k = 0; k < kVec; ++k) acc[i][k] = f[k] > 0.f ? acc[i][k] : 0.f;
           }
         }
-        V::store(ob + (size_t)i * LPR * VB, acc[i]);
+        if (OUTF32) store_f32_stream<kVec>(ob + (size_t)i * LPR * VB * kOutMul, acc[i]);
+        else V::store(ob + (size_t)i * LPR * VB, acc[i]);
       }
 #pragma unroll
       for (int k = 0; k < kVec; ++k) acc[i][k] = 0.f;
@@ -327,8 +364,9 @@ __global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(
 
 // Second stage for long rows: sum the slices' fp32 partials in slice order (deterministic), then the
 // mode's epilogue (mean / scale / accumulate).  One CTA per long row.
-template <typename T, int MODE>
+template <typename T, int MODE, bool OUTF32 = false>
 __global__ void __launch_bounds__(128) gather_combine_long(const GatherArgs a) {
+  using TO = typename std::conditional<OUTF32, float, T>::type;
   const int i = blockIdx.x;
   const int64_t orow = a.long_rows[i];
   const int s0 = a.long_ptr[i], s1 = a.long_ptr[i + 1];
@@ -336,7 +374,7 @@ __global__ void __launch_bounds__(128) gather_combine_long(const GatherArgs a) {
   const float post = (MODE != kMean && a.scale) ? __ldg(a.scale) : 1.f;
   const float cntf = (float)max(a.rowptr_orig[orow + 1] - a.rowptr_orig[orow], 1);
   if (MODE == kMean && threadIdx.x == 0 && a.inv_deg_out) a.inv_deg_out[orow] = __fdiv_rn(1.f, cntf);
-  T* out = reinterpret_cast<T*>(a.out) + (size_t)orow * feat;
+  TO* out = reinterpret_cast<TO*>(a.out) + (size_t)orow * feat;
   for (int f = threadIdx.x; f < feat; f += blockDim.x) {
     float s = 0.f;
     for (int sl = s0; sl < s1; ++sl) s += a.partial[(size_t)sl * feat + f];
@@ -347,26 +385,26 @@ __global__ void __launch_bounds__(128) gather_combine_long(const GatherArgs a) {
       if (a.accumulate) s += (float)out[f];
       if (a.relu_of && !((float)reinterpret_cast<const T*>(a.relu_of)[(size_t)orow * feat + f] > 0.f)) s = 0.f;
     }
-    out[f] = (T)s;
+    out[f] = (TO)s;
   }
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool OUTF32 = false>
 int launch_gather(const GatherArgs& a, cudaStream_t st) {
   if (a.n_rows == 0) return TRG_OK;
   const int rv = a.row_vecs;
 #define TRG_GATHER_CASE(LPR, VPL)                                                         \
   {                                                                                       \
     const int64_t grid = ceil_div<int64_t>(a.n_rows, kThreads / LPR);                     \
-    gather_reduce<T, LPR, VPL, MODE><<<(unsigned)grid, kThreads, 0, st>>>(a);             \
+    gather_reduce<T, LPR, VPL, MODE, OUTF32><<<(unsigned)grid, kThreads, 0, st>>>(a);             \
   }
 #define TRG_GATHER_SEG(LPR, VPL, R)                                                       \
   {                                                                                       \
     const int64_t grid = ceil_div<int64_t>(a.n_rows, (int64_t)(kThreads / LPR) * R);      \
     if (a.vinfo)                                                                          \
-      gather_reduce_seg<T, LPR, VPL, MODE, R, true><<<(unsigned)grid, kThreads, 0, st>>>(a);  \
+      gather_reduce_seg<T, LPR, VPL, MODE, R, true, 16, OUTF32><<<(unsigned)grid, kThreads, 0, st>>>(a);  \
     else                                                                                  \
-      gather_reduce_seg<T, LPR, VPL, MODE, R, false><<<(unsigned)grid, kThreads, 0, st>>>(a); \
+      gather_reduce_seg<T, LPR, VPL, MODE, R, false, 16, OUTF32><<<(unsigned)grid, kThreads, 0, st>>>(a); \
   }
 #define TRG_GATHER_SEG8()                                                                 \
   {                                                                                       \
@@ -374,9 +412,9 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
     b.row_vecs = a.row_vecs * 2;                                                          \
     const int64_t grid = ceil_div<int64_t>(b.n_rows, (int64_t)(kThreads / 32) * 8);       \
     if (b.vinfo)                                                                          \
-      gather_reduce_seg<T, 32, 1, MODE, 8, true, 8><<<(unsigned)grid, kThreads, 0, st>>>(b);  \
+      gather_reduce_seg<T, 32, 1, MODE, 8, true, 8, OUTF32><<<(unsigned)grid, kThreads, 0, st>>>(b);  \
     else                                                                                  \
-      gather_reduce_seg<T, 32, 1, MODE, 8, false, 8><<<(unsigned)grid, kThreads, 0, st>>>(b); \
+      gather_reduce_seg<T, 32, 1, MODE, 8, false, 8, OUTF32><<<(unsigned)grid, kThreads, 0, st>>>(b); \
   }
   if (rv <= 1) TRG_GATHER_CASE(1, 1)
   else if (rv <= 2) TRG_GATHER_CASE(2, 1)
@@ -397,7 +435,7 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
   count_launch();
   TRG_LAUNCH_OK();
   if (a.vinfo && a.n_long > 0) {
-    gather_combine_long<T, MODE><<<(unsigned)a.n_long, 128, 0, st>>>(a);
+    gather_combine_long<T, MODE, OUTF32><<<(unsigned)a.n_long, 128, 0, st>>>(a);
     count_launch();
     TRG_LAUNCH_OK();
   }
@@ -405,9 +443,19 @@ int launch_gather(const GatherArgs& a, cudaStream_t st) {
 }
 
 template <int MODE>
-int dispatch(const GatherArgs& a, int dtype, cudaStream_t st) {
+int dispatch(const GatherArgs& a, int dtype, int out_dtype, cudaStream_t st) {
+  if (out_dtype != dtype && !(MODE != kMean && dtype == TRG_BF16 && out_dtype == TRG_F32)) {
+    set_error("gather: out_dtype %d with dtype %d is not supported (fp32 output rows exist for bf16 sums only)",
+              out_dtype, dtype);
+    return TRG_E_UNSUPPORTED;
+  }
   if (dtype == TRG_F32) return launch_gather<float, MODE>(a, st);
-  if (dtype == TRG_BF16) return launch_gather<__nv_bfloat16, MODE>(a, st);
+  if (dtype == TRG_BF16) {
+    if constexpr (MODE != kMean) {
+      if (out_dtype == TRG_F32) return launch_gather<__nv_bfloat16, MODE, true>(a, st);
+    }
+    return launch_gather<__nv_bfloat16, MODE>(a, st);
+  }
   set_error("gather: unknown dtype %d", dtype);
   return TRG_E_ARG;
 }
@@ -457,12 +505,12 @@ extern "C" int trg_sage_agg_fwd(const int32_t* rowptr, const int32_t* col, const
   a.n_rows = n_dst;
   rc = apply_long(a, lr, rowptr, "trg_sage_agg_fwd");
   if (rc) return rc;
-  return dispatch<kMean>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch<kMean>(a, dtype, dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg,
                                 const void* g_mean, int64_t n_src, int32_t feat, int dtype,
-                                void* g_src_out, int accumulate, const void* relu_of,
+                                void* g_src_out, int out_dtype, int accumulate, const void* relu_of,
                                 const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_src >= 0, "trg_sage_agg_bwd: n_src < 0");
   if (n_src == 0) return TRG_OK;
@@ -476,12 +524,12 @@ extern "C" int trg_sage_agg_bwd(const int32_t* rowptr_t, const int32_t* col_t, c
   a.n_rows = n_src; a.accumulate = accumulate; a.relu_of = relu_of;
   rc = apply_long(a, lr, rowptr_t, "trg_sage_agg_bwd");
   if (rc) return rc;
-  return dispatch<kNbrScale>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch<kNbrScale>(a, dtype, out_dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* eid,
                                const float* coef, const float* scale, const void* x, int64_t n_rows,
-                               int32_t feat, int dtype, void* out, int accumulate, const void* relu_of,
+                               int32_t feat, int dtype, void* out, int out_dtype, int accumulate, const void* relu_of,
                                const trg_long_rows* lr, void* stream) {
   TRG_CHECK_ARG(n_rows >= 0, "trg_gather_wsum: n_rows < 0");
   if (n_rows == 0) return TRG_OK;
@@ -495,5 +543,5 @@ extern "C" int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const 
   a.n_rows = n_rows; a.accumulate = accumulate; a.relu_of = relu_of;
   rc = apply_long(a, lr, rowptr, "trg_gather_wsum");
   if (rc) return rc;
-  return dispatch<kEdgeCoef>(a, dtype, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch<kEdgeCoef>(a, dtype, out_dtype, reinterpret_cast<cudaStream_t>(stream));
 }

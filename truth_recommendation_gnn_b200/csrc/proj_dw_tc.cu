@@ -377,11 +377,8 @@ int launch_dw(const DwParams& p, int grid, cudaStream_t st) {
   int need_cols = F32 ? 512 : p.total_cols, tmem_cols = 32;
   while (tmem_cols < need_cols) tmem_cols <<= 1;
   const int smem = n_stages * stage_bytes + kOnesBytes + 1024 + 256;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    TRG_CUDA(cudaFuncSetAttribute(proj_dw_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  static SmemAttrState attr;
+  TRG_CUDA(ensure_dyn_smem(proj_dw_kernel<F32>, smem, attr));
   proj_dw_kernel<F32><<<grid, 256, smem, st>>>(p, stage_bytes, n_stages, tmem_cols);
   count_launch();
   TRG_LAUNCH_OK();
@@ -399,7 +396,7 @@ int proj_tc_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_term
   }
   const int kr = f32 ? 16 : 32;
   const int epc = f32 ? 32 : 64;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, (n_rows + kr - 1) / kr));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sms(), (n_rows + kr - 1) / kr));
   int64_t rows_per_cta = (n_rows + grid - 1) / grid;
   rows_per_cta = (rows_per_cta + kr - 1) / kr * kr;
 
@@ -516,7 +513,7 @@ __global__ void __launch_bounds__(256) colsum_simt(const T* __restrict__ dz, lon
 int proj_simt_bwd_weight(const void* dz, const trg_proj_dw_term* terms, int n_terms, float* db,
                          int64_t n_rows, int hidden, int dtype, void* ws, size_t ws_bytes,
                          cudaStream_t st) {
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, (n_rows + 63) / 64));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sms(), (n_rows + 63) / 64));
   const int64_t rows_per_cta = (n_rows + grid - 1) / grid;
   float* partial = reinterpret_cast<float*>(ws);
   for (int t = 0; t <= n_terms; ++t) {

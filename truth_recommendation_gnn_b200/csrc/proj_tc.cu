@@ -580,14 +580,10 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, u
 template <bool F32, int BN>
 int launch_cfg(const GemmParams& p, cudaStream_t st) {
   using C = Cfg<F32, BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRG_CUDA(cudaFuncSetAttribute(proj_tc_kernel<F32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmemBytes));
-    attr_set = true;
-  }
+  static SmemAttrState attr;
+  TRG_CUDA(ensure_dyn_smem(proj_tc_kernel<F32, BN>, C::kSmemBytes, attr));
   const long long n_tiles = (p.n_rows + BM - 1) / BM;
-  const int grid = (int)std::min<long long>(n_tiles, kNumSMs);
+  const int grid = (int)std::min<long long>(n_tiles, grid_sms());
   proj_tc_kernel<F32, BN><<<grid, C::kThreads, C::kSmemBytes, st>>>(p);
   count_launch();
   TRG_LAUNCH_OK();
@@ -597,28 +593,17 @@ int launch_cfg(const GemmParams& p, cudaStream_t st) {
 template <int BN>
 int launch_cfg_a(const GemmParams& p, cudaStream_t st) {
   using C = CfgA<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRG_CUDA(cudaFuncSetAttribute(proj_tc_f32a_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmemBytes));
-    attr_set = true;
-  }
+  static SmemAttrState attr;
+  TRG_CUDA(ensure_dyn_smem(proj_tc_f32a_kernel<BN>, C::kSmemBytes, attr));
   const long long n_tiles = (p.n_rows + BM - 1) / BM;
-  const int grid = (int)std::min<long long>(n_tiles, kNumSMs);
+  const int grid = (int)std::min<long long>(n_tiles, grid_sms());
   proj_tc_f32a_kernel<BN><<<grid, C::kThreads, C::kSmemBytes, st>>>(p);
   count_launch();
   TRG_LAUNCH_OK();
   return TRG_OK;
 }
 
-static bool use_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TRG_PROJ_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
+static bool use_v1() { return debug_env_int("TRG_PROJ_V1", 0) == 1; }   // A/B, TRG_DEBUG builds only
 
 int launch_gemm(const GemmParams& p, bool f32, int bn, cudaStream_t st) {
   if (f32 && !use_v1()) {       // split A operand in tensor memory (hidden <= 128: TMEM budget)

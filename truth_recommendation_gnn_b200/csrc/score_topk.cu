@@ -314,7 +314,8 @@ extern "C" int trg_score_topk(const void* q, const void* cat, int64_t n_query, i
   a.part_ids = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) +
                                             align_up((size_t)n_query * a.n_splits * kk * 4, 256));
   const size_t smem = score_smem_bytes(hidden);
-  TRG_CUDA(cudaFuncSetAttribute(score_topk_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static SmemAttrState attr;
+  TRG_CUDA(ensure_dyn_smem(score_topk_f32, (int)smem, attr));
   dim3 grid((unsigned)ceil_div<int64_t>(n_query, kBQ), (unsigned)a.n_splits);
   score_topk_f32<<<grid, kThreads, smem, st>>>(a);
   count_launch();

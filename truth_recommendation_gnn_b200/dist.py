@@ -88,6 +88,22 @@ class ShardedGraph:
             dist.all_reduce(wsum)
         self.wbar = (wsum[0] / wsum[1]).reshape(1).float().contiguous()
         self._layer0_src = None
+        self._neg_gen = None
+
+    def draw_negatives(self):
+        """``neg_p = torch.randint(0, num_posts, (E,))`` of train_gnn.py:272 for a step whose caller supplies
+        none.  Every rank must see the SAME array (each keeps the entries whose post it owns, and their union
+        has to be one negative per positive edge): it is drawn from a dedicated device generator seeded with
+        a value broadcast from rank 0 when first used and advanced identically on every rank afterwards --
+        never from the ranks' own default generators, whose states are unrelated."""
+        dev = self.pos_u_global.device
+        if self._neg_gen is None:
+            seed = torch.randint(0, 2**62, (1,), dtype=torch.int64)
+            if self.world > 1:
+                seed = seed.to(dev) if dist.get_backend() == "nccl" else seed
+                dist.broadcast(seed, src=0)
+            self._neg_gen = torch.Generator(device=dev).manual_seed(int(seed.item()))
+        return torch.randint(0, self.num_posts, (self.n_pos_global,), generator=self._neg_gen, device=dev)
 
     def local_negatives(self, neg_p_global):
         """This rank's share of ``neg_p = torch.randint(0, P, (E,))`` (train_gnn.py:272): the pairs
@@ -218,15 +234,16 @@ def train_step_sharded(model, optimizer, shard: ShardedGraph, neg_p_global=None,
                        ops=CUDA_OPS, loss_ops=CUDA_LOSS_OPS, return_tensor=False):
     """The body of ``train()`` (train_gnn.py:242-285) on a destination partition.  Every rank holds
     the same weights; the returned loss is the global loss (identical on all ranks).
-    ``neg_p_global``: the step's ``torch.randint(0, P, (E,))`` (same array on every rank), or
-    ``neg_p_local``: this rank's share already selected with ``shard.local_negatives``."""
+    ``neg_p_global``: the step's ``torch.randint(0, P, (E,))`` -- it MUST be the same array on every rank;
+    ``None`` draws it from the shard's rank-synchronised generator (``ShardedGraph.draw_negatives``) --
+    or ``neg_p_local``: this rank's share already selected with ``shard.local_negatives``."""
     model.train()
     optimizer.zero_grad()
     out = forward_sharded(model, shard, ops)
     user_full = all_gather_rows(out["user"])
     if neg_p_local is None:
         if neg_p_global is None:
-            neg_p_global = torch.randint(0, shard.num_posts, (shard.n_pos_global,), device=user_full.device)
+            neg_p_global = shard.draw_negatives()
         neg_p_local = shard.local_negatives(neg_p_global)
     loss_local = AnchoredLinkLossFn.apply(user_full, out["post"], neg_p_local, shard, loss_ops)
     loss_local.backward()

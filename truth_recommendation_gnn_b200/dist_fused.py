@@ -77,10 +77,15 @@ class CudaStepPrims:
         return _agg(rel, x_src)
 
     @staticmethod
-    def gather_sum(rel, which, x, out=None, accumulate=False, relu_of=None):
+    def gather_sum(rel, which, x, out=None, accumulate=False, relu_of=None, out_dtype=None):
         from .functional import sage_agg_bwd
         return sage_agg_bwd(rel.fwd if which == "fwd" else rel.bwd, None, x, out=out, accumulate=accumulate,
-                            relu_of=relu_of)
+                            relu_of=relu_of, out_dtype=out_dtype)
+
+    @staticmethod
+    def rows_finish(x, dtype, row_scale=None, add=None, relu_of=None):
+        from .functional import rows_finish
+        return rows_finish(x, dtype, row_scale=row_scale, add=add, relu_of=relu_of)
 
     @staticmethod
     def proj_fwd(terms, bias, relu):
@@ -109,17 +114,19 @@ class CudaStepPrims:
                                 coef_in_csr_order=coef_in_csr_order)
 
     @staticmethod
-    def wsum(csr, coef, x, out=None, accumulate=False):
+    def wsum(csr, coef, x, out=None, accumulate=False, out_dtype=None):
         from .functional import gather_wsum
-        return gather_wsum(csr, coef, x, out=out, accumulate=accumulate)
+        return gather_wsum(csr, coef, x, out=out, accumulate=accumulate, out_dtype=out_dtype)
 
 
 CUDA_STEP_PRIMS = CudaStepPrims()
 
 
-def _relu_gate(g, act):
-    """ReLU backward on owned rows (1/world of a table: small next to the gather kernels)."""
-    return torch.ops.aten.threshold_backward(g, act, 0)
+def transport_dtype(dtype):
+    """dtype in which partial sums cross NVLink: bf16 tables send fp32 partials (each rank's fp32
+    accumulation is NOT rounded before the cross-rank add; the owner rounds once, in ``rows_finish``), so
+    the sharded bf16 result has the single-GPU kernel's rounding behaviour.  fp32 tables: fp32."""
+    return torch.float32 if dtype == torch.bfloat16 else None
 
 
 def _accum(param, grad):
@@ -151,6 +158,8 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     rel_d = prel_d.rel                                  # rows ("fwd") = all users, sources = local posts
     hu, hp = shard.x_local["user"], shard.x_local["post"]
     n_u_pad = shard.cu * shard.world
+    dtype = hu.dtype
+    xfer = transport_dtype(dtype)
 
     # ---- forward ----
     saved = []
@@ -161,7 +170,7 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
             conv.lin_r.materialize(xd.size(-1))
         wd, ws = float(layer.w_direct), float(layer.w_social)
         ag = None if i == 0 else all_gather_rows_async(hu)
-        part = prims.gather_sum(rel_d, "fwd", hp)                       # [U_pad, F] partial sums  || all-gather
+        part = prims.gather_sum(rel_d, "fwd", hp, out_dtype=xfer)       # [U_pad, F] partial sums  || all-gather
         rs = reduce_scatter_rows_async(part)
         del part
         user_full = shard.layer0_sources()["user"] if i == 0 else ag.wait()
@@ -169,7 +178,7 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
         mean_e = prims.agg_mean(rel_e, user_full)
         del user_full
         hp_n = prims.proj_fwd([(mean_e, p.lin_l.weight, 1.0), (hp, p.lin_r.weight, 1.0)], p.lin_l.bias, True)
-        mean_d = rs.wait() * prel_d.inv_deg.to(hu.dtype)[:, None]
+        mean_d = prims.rows_finish(rs.wait(), hu.dtype, row_scale=prel_d.inv_deg)     # sum / global in-degree
         w_root = wd * d.lin_r.weight + ws * s.lin_r.weight
         b_user = wd * d.lin_l.bias + ws * s.lin_l.bias
         hu_n = prims.proj_fwd([(mean_d, d.lin_l.weight, wd), (mean_s, s.lin_l.weight, ws), (hu, w_root, 1.0)],
@@ -191,7 +200,7 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
                                           **({"coef_in_csr_order": True} if seq else {}))
     l_neg, c_neg, dz_p = prims.anchor_loss(neg_by_post, hp, user_full, e_glob, 0, shard.wbar, g_p, True)
     del user_full
-    g_uf = prims.wsum(st["pos_by_user_p" if seq else "pos_by_user"], c_pos, hp)     # dL/du partials, all users
+    g_uf = prims.wsum(st["pos_by_user_p" if seq else "pos_by_user"], c_pos, hp, out_dtype=xfer)   # dL/du partials, all users
     g_uf = prims.wsum(neg_by_user, c_neg, hp, out=g_uf, accumulate=True)
     pend_u = (reduce_scatter_rows_async(g_uf), None, hu)        # (partials in flight, local term, gate)
     loss_local = (l_pos + l_neg).reshape(())
@@ -208,13 +217,12 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
         g_uf = g_hp = None
         if li > 0:
             g_me, g_hp = prims.proj_bwd_input(dz_p, [(p.lin_l.weight, 1.0, rel_e.inv_deg), (p.lin_r.weight, 1.0, None)])
-            g_uf = prims.gather_sum(rel_e, "bwd", g_me)               # d user_full partials (engages^T)
+            g_uf = prims.gather_sum(rel_e, "bwd", g_me, out_dtype=xfer)      # d user_full partials (engages^T)
             del g_me
         del dz_p, mean_e
         rs, g_loc, act = pend_u
-        g = rs.wait()
-        dz_u = _relu_gate(g if g_loc is None else g_loc.add_(g), act)
-        del g, g_loc, act, pend_u
+        dz_u = prims.rows_finish(rs.wait(), dtype, add=g_loc, relu_of=act)     # (+ local term), ReLU backward
+        del g_loc, act, pend_u
         (dw_d, dw_s, dw_root), db_u = prims.proj_bwd_weight(dz_u, [(mean_d, wd), (mean_s, ws), (hu_in, 1.0)], True)
         del mean_d, mean_s
         _accum(d.lin_l.weight, dw_d)
@@ -248,8 +256,7 @@ def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global
     optimizer.zero_grad()
     if neg_p_local is None:
         if neg_p_global is None:
-            neg_p_global = torch.randint(0, shard.num_posts, (shard.n_pos_global,),
-                                         device=shard.x_local["user"].device)
+            neg_p_global = shard.draw_negatives()          # rank-synchronised generator: same array everywhere
         neg_p_local = shard.local_negatives(neg_p_global)
     neg_ready = None
     if not neg_p_local.is_cuda and shard.x_local["user"].is_cuda:

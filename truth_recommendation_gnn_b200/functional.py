@@ -13,9 +13,11 @@ from . import _lib
 from .graph import CSR, RelationGraph, build_csr
 
 
-def _long_rows_arg(csr: CSR, feat: int, dev):
-    """ctypes ``trg_long_rows`` (+ the tensors it points to, to keep them alive) or ``(None, None)``."""
-    lr = csr.long_rows() if feat * 4 >= 80 else None
+def _long_rows_arg(csr: CSR, feat: int, dev, elem_size: int = 4):
+    """ctypes ``trg_long_rows`` (+ the tensors it points to, to keep them alive) or ``(None, None)``.
+    Splitting needs rows of at least 80 bytes in the table's own dtype (gather.cu ``apply_long``); narrower
+    rows run unsplit -- splitting is a load-balance measure, results do not depend on it."""
+    lr = csr.long_rows() if feat * elem_size >= 80 else None
     if lr is None:
         return None, None
     partial = torch.empty(lr.n_slots, feat, dtype=torch.float32, device=dev)
@@ -44,41 +46,54 @@ def sage_agg_fwd(csr: CSR, x_src: torch.Tensor, want_inv_deg: bool = True):
     if csr.n_rows:
         rb = x_src.size(1) * x_src.element_size()
         nbytes = csr.n_edges * (rb + 4) + 4 * (csr.n_rows + 1) + csr.n_rows * rb
-        lr, keep = _long_rows_arg(csr, x_src.size(1), x_src.device)
+        lr, keep = _long_rows_arg(csr, x_src.size(1), x_src.device, x_src.element_size())
         _lib.call("trg_sage_agg_fwd", nbytes, lib.trg_sage_agg_fwd,
                   _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(x_src), csr.n_rows, x_src.size(1),
                   _lib.dtype_code(x_src.dtype), _lib.ptr(out), _lib.ptr(inv_deg), lr, _lib.stream())
     return out, inv_deg
 
 
-def _check_epilogue(out, relu_of, n_rows, x, who):
-    for t, what in ((out, "out"), (relu_of, "relu_of")):
-        if t is not None and (t.shape != (n_rows, x.size(1)) or t.dtype != x.dtype or not t.is_contiguous()
+def _check_epilogue(out, relu_of, n_rows, x, who, out_dtype=None):
+    for t, what, dt in ((out, "out", out_dtype or x.dtype), (relu_of, "relu_of", x.dtype)):
+        if t is not None and (t.shape != (n_rows, x.size(1)) or t.dtype != dt or not t.is_contiguous()
                               or t.device != x.device):
-            raise _lib.TrgError(f"{who}: {what} must be a contiguous [{n_rows}, {x.size(1)}] {x.dtype} tensor")
+            raise _lib.TrgError(f"{who}: {what} must be a contiguous [{n_rows}, {x.size(1)}] {dt} tensor")
 
 
-def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor, out=None, accumulate=False, relu_of=None):
+def _out_dtype(x, out, out_dtype):
+    """``out_dtype``: None = the table's dtype; ``torch.float32`` with a bf16 table = fp32 sum rows (partials
+    a multi-GPU run reduces across ranks before the single rounding to bf16)."""
+    if out_dtype is None:
+        out_dtype = out.dtype if out is not None else x.dtype
+    if out_dtype != x.dtype and not (x.dtype == torch.bfloat16 and out_dtype == torch.float32):
+        raise _lib.TrgError(f"output dtype {out_dtype} is not supported for a {x.dtype} table")
+    return out_dtype
+
+
+def sage_agg_bwd(csr_t: CSR, inv_deg, g_mean: torch.Tensor, out=None, accumulate=False, relu_of=None,
+                 out_dtype=None):
     """Atomic-free gradient w.r.t. the source table through the transposed CSR.  ``out`` +
     ``accumulate`` add to gradient rows already computed (a table feeding several relations);
     ``relu_of`` gates the final rows by ``relu_of > 0`` (the producing layer's ReLU backward)."""
     lib = _lib.load()
     g_mean = g_mean.contiguous()
     _check_rows(g_mean, "sage_agg_bwd")
-    _check_epilogue(out, relu_of, csr_t.n_rows, g_mean, "sage_agg_bwd")
+    out_dtype = _out_dtype(g_mean, out, out_dtype)
+    _check_epilogue(out, relu_of, csr_t.n_rows, g_mean, "sage_agg_bwd", out_dtype)
     if out is None:
-        out = torch.empty(csr_t.n_rows, g_mean.size(1), dtype=g_mean.dtype, device=g_mean.device)
+        out = torch.empty(csr_t.n_rows, g_mean.size(1), dtype=out_dtype, device=g_mean.device)
         accumulate = False
     if csr_t.n_rows:
         rb = g_mean.size(1) * g_mean.element_size()
+        ob = g_mean.size(1) * out.element_size()
         nbytes = (csr_t.n_edges * (rb + 4) + 4 * (csr_t.n_rows + 1)
-                  + csr_t.n_rows * rb * (1 + bool(accumulate) + (relu_of is not None))
+                  + csr_t.n_rows * (ob * (1 + bool(accumulate)) + rb * (relu_of is not None))
                   + (4 * csr_t.n_cols if inv_deg is not None else 0))
-        lr, keep = _long_rows_arg(csr_t, g_mean.size(1), g_mean.device)
+        lr, keep = _long_rows_arg(csr_t, g_mean.size(1), g_mean.device, g_mean.element_size())
         _lib.call("trg_sage_agg_bwd", nbytes, lib.trg_sage_agg_bwd,
                   _lib.ptr(csr_t.rowptr), _lib.ptr(csr_t.col), _lib.ptr(inv_deg), _lib.ptr(g_mean),
                   csr_t.n_rows, g_mean.size(1), _lib.dtype_code(g_mean.dtype), _lib.ptr(out),
-                  1 if accumulate else 0, _lib.ptr(relu_of), lr, _lib.stream())
+                  _lib.dtype_code(out_dtype), 1 if accumulate else 0, _lib.ptr(relu_of), lr, _lib.stream())
     return out
 
 
@@ -112,23 +127,50 @@ def sage_mean_aggregate(x_src: torch.Tensor, rel: RelationGraph, grad_prescaled:
 # ------------------------------------------------------------------------------------------
 # generic weighted gather-sum
 # ------------------------------------------------------------------------------------------
-def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulate=False, relu_of=None):
+def gather_wsum(csr: CSR, coef, x: torch.Tensor, scale=None, out=None, accumulate=False, relu_of=None,
+                out_dtype=None):
     lib = _lib.load()
     x = x.contiguous()
     _check_rows(x, "gather_wsum")
-    _check_epilogue(out, relu_of, csr.n_rows, x, "gather_wsum")
+    out_dtype = _out_dtype(x, out, out_dtype)
+    _check_epilogue(out, relu_of, csr.n_rows, x, "gather_wsum", out_dtype)
     if out is None:
-        out = torch.empty(csr.n_rows, x.size(1), dtype=x.dtype, device=x.device)
+        out = torch.empty(csr.n_rows, x.size(1), dtype=out_dtype, device=x.device)
         accumulate = False
     if csr.n_rows:
         rb = x.size(1) * x.element_size()
+        ob = x.size(1) * out.element_size()
         nbytes = (csr.n_edges * (rb + 12) + 4 * (csr.n_rows + 1)
-                  + csr.n_rows * rb * (1 + bool(accumulate) + (relu_of is not None)))
-        lr, keep = _long_rows_arg(csr, x.size(1), x.device)
+                  + csr.n_rows * (ob * (1 + bool(accumulate)) + rb * (relu_of is not None)))
+        lr, keep = _long_rows_arg(csr, x.size(1), x.device, x.element_size())
         _lib.call("trg_gather_wsum", nbytes, lib.trg_gather_wsum,
                   _lib.ptr(csr.rowptr), _lib.ptr(csr.col), _lib.ptr(csr.eid), _lib.ptr(coef),
                   _lib.ptr(scale), _lib.ptr(x), csr.n_rows, x.size(1), _lib.dtype_code(x.dtype),
-                  _lib.ptr(out), 1 if accumulate else 0, _lib.ptr(relu_of), lr, _lib.stream())
+                  _lib.ptr(out), _lib.dtype_code(out_dtype), 1 if accumulate else 0, _lib.ptr(relu_of), lr,
+                  _lib.stream())
+    return out
+
+
+def rows_finish(x, dtype, row_scale=None, add=None, relu_of=None, out=None):
+    """``out = gate(row_scale[:, None] * x + add)`` rounded once to ``dtype`` (``trg_rows_finish``): the
+    owned rows of a table reduced across GPUs -- 1/deg of a source-partitioned mean, the local gradient
+    term, the ReLU backward -- in one pass.  ``x`` is fp32 (fp32-transported partial sums) or ``dtype``."""
+    lib = _lib.load()
+    x = x.contiguous()
+    n, feat = x.shape
+    if x.dtype != dtype and x.dtype != torch.float32:
+        raise _lib.TrgError(f"rows_finish: input must be {dtype} or float32, got {x.dtype}")
+    for t, what in ((add, "add"), (relu_of, "relu_of"), (out, "out")):
+        if t is not None and (t.shape != x.shape or t.dtype != dtype or not t.is_contiguous()):
+            raise _lib.TrgError(f"rows_finish: {what} must be a contiguous [{n}, {feat}] {dtype} tensor")
+    if out is None:
+        out = torch.empty(n, feat, dtype=dtype, device=x.device)
+    _check_rows(out, "rows_finish")
+    rs = row_scale.float().contiguous() if row_scale is not None else None
+    es = out.element_size()
+    nbytes = n * feat * (x.element_size() + es * (1 + (add is not None) + (relu_of is not None)))
+    _lib.call("trg_rows_finish", nbytes, lib.trg_rows_finish, _lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(rs),
+              _lib.ptr(add), _lib.ptr(relu_of), n, feat, _lib.dtype_code(dtype), _lib.ptr(out), _lib.stream())
     return out
 
 
@@ -276,6 +318,13 @@ class LinkBCEFn(torch.autograd.Function):
             ls.eid_long = ls.by_user.eid.long()
         e_scale = int(getattr(ls, "n_edges_scale", ls.n_edges))
         bu = ls.by_user
+        # the negatives grouped by post with this step's stable sort (needed by the backward); built first
+        # because its histogram pass is also the range check of caller-supplied ids (K0 aborts on an id
+        # outside [0, P) before any kernel uses it as a row index)
+        ctx.neg_by_post = None
+        if want and ls.n_edges:
+            ctx.neg_by_post = build_csr(ls.train_edge_index[0], neg_p, ls.num_posts, ls.num_users, validate=False,
+                                        per_step=True)
         col_neg = neg_p.index_select(0, ls.eid_long).int()     # negatives in the by-user edge order
         neg_csr = CSR(bu.rowptr, col_neg, bu.eid, bu.n_rows, bu.n_cols)
         l_pos, c_pos, g_u = edge_anchor_loss(bu, user_emb, post_emb, e_scale, 1, ls.wbar, want, None)
@@ -295,12 +344,11 @@ class LinkBCEFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             g_user = g_u * g.to(g_u.dtype)
         if ctx.needs_input_grad[1]:
-            pos_u = ls.train_edge_index[0]
             # dloss/dp = sum over positive edges of the post (static structure) ...
             g_post = gather_wsum(ls.by_post, c_pos, user_emb, scale=g)
-            # ... plus the sampled negatives, grouped by post with this step's stable sort
-            neg_csr = build_csr(pos_u, neg_p, ls.num_posts, ls.num_users, validate=False, per_step=True)
-            gather_wsum(neg_csr, c_neg, user_emb, scale=g, out=g_post, accumulate=True)
+            # ... plus the sampled negatives, grouped by post (this step's stable sort, built in forward)
+            if ctx.neg_by_post is not None:
+                gather_wsum(ctx.neg_by_post, c_neg, user_emb, scale=g, out=g_post, accumulate=True)
         return g_user, g_post, None, None
 
 

@@ -114,12 +114,14 @@ def loss_and_grads(model, x_dict, edge_index_dict, train_edge_index, interaction
     # up through edge ids that ARE by-user positions (static remap for the positives; for the negatives
     # the per-step sort is run on the by-user-ordered arrays, so its edge ids come out that way)
     col_neg64 = neg_p.index_select(0, ls.eid_long)
+    # this step's by-post grouping first: its histogram pass is also the range check of the caller's
+    # negatives (an id outside [0, P) aborts there, before any kernel uses it as a row index)
+    neg_by_post = build_csr(ls.user_of_u, col_neg64, n_p, n_u, validate=False, per_step=True)
     neg_by_user = CSR(bu.rowptr, col_neg64.int(), bu.eid, bu.n_rows, bu.n_cols)
     l_pos, c_pos, dz_u = edge_anchor_loss(bu, hu, hp, ls.n_edges, 1, ls.wbar, True, None, coef_in_csr_order=True)
     l_neg, c_neg, dz_u = edge_anchor_loss(neg_by_user, hu, hp, ls.n_edges, 0, ls.wbar, True, dz_u,
                                           relu_gate=True, coef_in_csr_order=True)
     dz_p = gather_wsum(ls.by_post_u, c_pos, hu)
-    neg_by_post = build_csr(ls.user_of_u, col_neg64, n_p, n_u, validate=False, per_step=True)
     gather_wsum(neg_by_post, c_neg, hu, out=dz_p, accumulate=True, relu_of=hp)
     del col_neg64
     loss = (l_pos + l_neg).reshape(())

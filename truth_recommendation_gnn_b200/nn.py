@@ -110,12 +110,12 @@ class SAGEConv(torch.nn.Module):
         self.lin_l.reset_parameters()
         self.lin_r.reset_parameters()
 
-    def aggregate(self, x_src, edge_index, n_dst):
-        """K0 (cached) + K1: mean of in-neighbour rows."""
-        rel = relation_graph(edge_index, x_src.size(0), n_dst)
-        return sage_mean_aggregate(x_src, rel)
-
     def forward(self, x, edge_index, size=None):
+        """K0 (cached) + K1 mean aggregation, then ``lin_l(mean) + lin_r(x_dst)`` as ONE K3 launch over the
+        concatenated K (bias in the epilogue, no ReLU: the caller applies its own, train_gnn.py:187-198).
+        Swapping the import at train_gnn.py:6 alone therefore leaves no GEMM of the conv on cuBLAS; the
+        gradient of the mean comes back pre-scaled by 1/deg (fused into the K3 input-gradient epilogue), so
+        the aggregation backward is a plain transposed gather-sum (K2)."""
         if isinstance(x, torch.Tensor):
             x = (x, x)
         x_src, x_dst = x
@@ -123,8 +123,10 @@ class SAGEConv(torch.nn.Module):
             raise _lib.TrgError("SAGEConv (B200) needs CUDA tensors; there is no CPU fallback")
         self.lin_l.materialize(x_src.size(-1))
         self.lin_r.materialize(x_dst.size(-1))
-        mean = self.aggregate(x_src, edge_index, x_dst.size(0))
-        return self.lin_l(mean) + self.lin_r(x_dst)
+        rel = relation_graph(edge_index, x_src.size(0), x_dst.size(0))
+        mean = sage_mean_aggregate(x_src, rel, True)
+        return fused_projection([(mean, self.lin_l.weight, 1.0), (x_dst, self.lin_r.weight, 1.0)],
+                                self.lin_l.bias, relu=False, row_scales=(rel.inv_deg, None))
 
     def __repr__(self):
         return f"SAGEConv({self.in_channels}, {self.out_channels}, aggr=mean)"
@@ -198,11 +200,11 @@ class CudaOps:
         return sage_mean_aggregate(x_src, rel, True)
 
     @staticmethod
-    def gather_sum(rel, which, x):
+    def gather_sum(rel, which, x, out_dtype=None):
         """Plain segmented gather-sum over the forward ("fwd": rows = destinations) or transposed
         ("bwd": rows = sources) CSR of a relation -- K2 without the 1/deg scale."""
         from .functional import sage_agg_bwd
-        return sage_agg_bwd(rel.fwd if which == "fwd" else rel.bwd, None, x)
+        return sage_agg_bwd(rel.fwd if which == "fwd" else rel.bwd, None, x, out_dtype=out_dtype)
 
     @staticmethod
     def project(terms, bias, relu, scale_rels):
