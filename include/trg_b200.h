@@ -55,6 +55,18 @@ int trg_csr_build(const int64_t* other, const int64_t* key, int64_t n_edges, int
                   int32_t* rowptr /* [n_key+1] */, int32_t* col /* [E] */, int32_t* eid /* [E] */,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Stable range selection without host synchronisation (multi-GPU: the share of this step's sampled
+ * negatives, train_gnn.py:272, whose post this rank owns).  key_out / other_out receive the pairs
+ * (key - lo, other) with lo <= key < hi in input order, then (pad_key, pad_other) up to `capacity` entries;
+ * count_out[0] = the number selected.  The consumers (trg_csr_build with n_key + 1 rows) take `capacity` as
+ * their edge count, so no size ever travels to the host; the padding lands in the sentinel row.  More than
+ * `capacity` selected entries abort the kernel (message + trap), never truncate silently. */
+size_t trg_select_range_workspace_bytes(int64_t n);
+int trg_select_range(const int64_t* key, const int64_t* other, int64_t n, int64_t lo, int64_t hi,
+                     int64_t capacity, int64_t pad_key, int64_t pad_other,
+                     int64_t* key_out /* [capacity] */, int64_t* other_out /* [capacity] */,
+                     int32_t* count_out /* [1] */, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Long-row splitting for skewed degree distributions (all optional: pass NULL when no row is long).
  * Rows longer than the caller's threshold T are cut into <= T-edge slices ("virtual rows"); slices
  * accumulate raw fp32 partial sums which a second small kernel adds up in slice order, so the result

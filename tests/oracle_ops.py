@@ -124,6 +124,10 @@ class OracleStepPrims:
     csr = staticmethod(OracleLossOps.csr)
 
     @staticmethod
+    def select_negatives(shard, neg_p_global, capacity=None):
+        return shard.local_negatives(neg_p_global)        # host logic under test: exact selection
+
+    @staticmethod
     def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate):
         loss, coef, g = OracleLossOps.anchor_loss(csr, anchor, gathered, n_edges, label, wbar, True, g_anchor)
         if relu_gate:

@@ -49,6 +49,21 @@ def _worker(rank, world, port, q, fused=False):
         qv, cat = synth.synth_queries(7, P, H, zero_frac=0.2)
         cat_local = cat[shard.p0:shard.p1].contiguous()
         rv, ri = tdist.recommend_sharded(qv, cat_local, 10, shard.p0, oracle_ops.score_topk, oracle_ops.merge)
+        # a counter-based graph sharded WITHOUT materialising it == the partition of the materialised graph
+        cg = synth.CounterGraph(U, P, EE, ES, H, seed=3)
+        gm = cg.materialize()
+        sa = tdist.ShardedGraph(gm.x_dict, gm.edge_index_dict, gm.train_edge_index, gm.interaction_type_tensor, U, P)
+        sb = tdist.ShardedGraph.from_generator(cg, "cpu", chunk=777)
+        for t in ("user", "post"):
+            assert torch.equal(sa.x_local[t], sb.x_local[t]), t
+        for rel in sa.rels:
+            ra, rb = sa.rels[rel], sb.rels[rel]
+            if isinstance(ra, trg.graph.PushRelation):
+                assert torch.equal(ra.inv_deg, rb.inv_deg)
+                ra, rb = ra.rel, rb.rel
+            assert torch.equal(ra.edge_index, rb.edge_index) and (ra.n_src, ra.n_dst) == (rb.n_src, rb.n_dst), rel
+        assert torch.equal(sa.pos_local, sb.pos_local) and torch.equal(sa.pos_u_global, sb.pos_u_global)
+        assert torch.equal(sa.wbar, sb.wbar) and sa.n_pos_global == sb.n_pos_global
         # negatives drawn inside the step (neg_p_global=None) must be ONE array shared by all ranks
         n1, n2 = shard.draw_negatives(), shard.draw_negatives()
         assert n1.shape == (EE,) and int(n1.min()) >= 0 and int(n1.max()) < P and not torch.equal(n1, n2)

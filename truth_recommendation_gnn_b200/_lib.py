@@ -43,6 +43,8 @@ SIGNATURES = {
     "trg_launch_count": (_i64, []),
     "trg_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "trg_csr_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "trg_select_range_workspace_bytes": (_sz, [_i64]),
+    "trg_select_range": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "trg_sage_agg_fwd": (_int, [_vp, _vp, _vp, _i64, _i32, _int, _vp, _vp, ctypes.POINTER(TrgLongRows), _vp]),
     "trg_sage_agg_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int, _int, _vp,
                                 ctypes.POINTER(TrgLongRows), _vp]),

@@ -128,6 +128,99 @@ __global__ void __launch_bounds__(kThreads) count_keys(const long long* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// stable range selection (multi-GPU: this rank's share of the step's negatives, train_gnn.py:272)
+// ---------------------------------------------------------------------------------------------
+// out = the (key - lo, other) pairs with lo <= key < hi, in input order, padded to `capacity` entries with
+// (pad_key, pad_other).  No host synchronisation: the consumers take `capacity` as their edge count and the
+// padding lands in a sentinel row past the last real one.  Three launches: per-tile counts, scan of the
+// tile counts (also publishes the total and aborts on overflow), stable scatter + padding.
+__global__ void __launch_bounds__(kThreads) select_count(const long long* __restrict__ key, int64_t n,
+                                                         long long lo, long long hi, int* __restrict__ tile_counts) {
+  __shared__ int warp_sums[kWarps];
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    const int64_t idx = base + (int64_t)i * kThreads + threadIdx.x;
+    if (idx < n) {
+      const long long k = ldg_stream(key + idx);
+      c += (k >= lo && k < hi) ? 1 : 0;
+    }
+  }
+  int total;
+  block_exclusive_scan<kWarps>(c, warp_sums, total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) select_offsets(int* __restrict__ tile_counts, int n_tiles,
+                                                       long long capacity, int* __restrict__ count_out) {
+  __shared__ int warp_sums[32];
+  int carry = 0;
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < n_tiles ? tile_counts[idx] : 0;
+    int total;
+    const int ex = block_exclusive_scan<32>(v, warp_sums, total);
+    if (idx < n_tiles) tile_counts[idx] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    *count_out = carry;
+    if ((long long)carry > capacity) {
+      printf("trg_select_range: %d selected entries exceed the capacity %lld (negatives far from uniform? pass a larger "
+             "capacity)\n", carry, capacity);
+      __trap();
+    }
+  }
+}
+
+// warp w owns the contiguous span [w * 512, w * 512 + 512) of the tile, walked 32 keys at a time: the output
+// position of a selected key = tile offset + earlier warps + earlier rounds + lower lanes (ballot) -> stable.
+__global__ void __launch_bounds__(kThreads)
+    select_scatter(const long long* __restrict__ key, const long long* __restrict__ other, int64_t n, long long lo,
+                   long long hi, const int* __restrict__ tile_offsets, const int* __restrict__ count,
+                   long long capacity, long long pad_key, long long pad_other, long long* __restrict__ key_out,
+                   long long* __restrict__ other_out) {
+  __shared__ int wtot[kWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * kTile + (int64_t)w * (kItems * 32);
+  long long kv[kItems];
+  unsigned sel[kItems];
+  int mine = 0;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int64_t idx = wbase + r * 32 + lane;
+    kv[r] = idx < n ? ldg_stream(key + idx) : lo - 1;
+    const bool in = kv[r] >= lo && kv[r] < hi;
+    sel[r] = __ballot_sync(0xffffffffu, in);
+    mine += __popc(sel[r]);
+  }
+  if (lane == 0) wtot[w] = mine;      // every lane holds the warp total (ballots are warp-wide)
+  __syncthreads();
+  int run = tile_offsets[blockIdx.x];
+  for (int i = 0; i < w; ++i) run += wtot[i];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    if ((sel[r] >> lane) & 1u) {
+      const int dest = run + __popc(sel[r] & ((1u << lane) - 1u));
+      if (dest < capacity) {
+        key_out[dest] = kv[r] - lo;
+        other_out[dest] = ldg_stream(other + wbase + r * 32 + lane);
+      }
+    }
+    run += __popc(sel[r]);
+  }
+  // padding [count, capacity): spread over the whole grid
+  const long long cnt = *count;
+  for (long long i = cnt + (long long)blockIdx.x * kThreads + threadIdx.x; i < capacity;
+       i += (long long)gridDim.x * kThreads) {
+    key_out[i] = pad_key;
+    other_out[i] = pad_other;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // one LSD pass: per-CTA digit histogram -> global scan -> stable scatter
 // ---------------------------------------------------------------------------------------------
@@ -344,5 +437,35 @@ extern "C" int trg_csr_build(const int64_t* other, const int64_t* key, int64_t e
     count_launch();
     TRG_LAUNCH_OK();
   }
+  return TRG_OK;
+}
+
+extern "C" size_t trg_select_range_workspace_bytes(int64_t n) {
+  if (n < 0) return 0;
+  return align_up((size_t)(ceil_div<int64_t>(n > 0 ? n : 1, kTile) + 1) * 4, 256);
+}
+
+extern "C" int trg_select_range(const int64_t* key, const int64_t* other, int64_t n, int64_t lo, int64_t hi,
+                                int64_t capacity, int64_t pad_key, int64_t pad_other, int64_t* key_out,
+                                int64_t* other_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  TRG_CHECK_ARG(n >= 0 && capacity >= 0 && lo <= hi, "trg_select_range: bad sizes");
+  TRG_CHECK_ARG(n < ((int64_t)1 << 31) && capacity < ((int64_t)1 << 31), "trg_select_range: sizes exceed int32 range");
+  TRG_CHECK_ARG(count_out && (capacity == 0 || (key_out && other_out)), "trg_select_range: NULL outputs");
+  TRG_CHECK_ARG(n == 0 || (key && other), "trg_select_range: NULL inputs with n > 0");
+  if (workspace == nullptr || workspace_bytes < trg_select_range_workspace_bytes(n)) {
+    set_error("trg_select_range: workspace %zu < required %zu", workspace_bytes, trg_select_range_workspace_bytes(n));
+    return TRG_E_WORKSPACE;
+  }
+  int* tile_counts = reinterpret_cast<int*>(workspace);
+  const int n_tiles = (int)ceil_div<int64_t>(n > 0 ? n : 1, kTile);
+  select_count<<<n_tiles, kThreads, 0, st>>>((const long long*)key, n, lo, hi, tile_counts);
+  select_offsets<<<1, 1024, 0, st>>>(tile_counts, n_tiles, capacity, count_out);
+  select_scatter<<<n_tiles, kThreads, 0, st>>>((const long long*)key, (const long long*)other, n, lo, hi, tile_counts,
+                                               count_out, capacity, pad_key, pad_other, (long long*)key_out,
+                                               (long long*)other_out);
+  count_launch(3);
+  TRG_LAUNCH_OK();
   return TRG_OK;
 }

@@ -111,11 +111,126 @@ class ShardedGraph:
         m = (neg_p_global >= self.p0) & (neg_p_global < self.p1)
         return torch.stack([self.pos_u_global[m], neg_p_global[m] - self.p0]).contiguous()
 
+    @classmethod
+    def from_generator(cls, cg, device, dtype=torch.float32, rank=None, world=None, chunk=32_000_000):
+        """This rank's share of a counter-based graph (``synth.CounterGraph``), produced ON THIS DEVICE without
+        the full graph ever existing anywhere: the edge streams are generated ``chunk`` edges at a time and
+        filtered by ownership, feature rows are generated for the owned ranges only.  Same attributes, same
+        edge order and therefore bit-identical structures as ``ShardedGraph(cg.materialize(...))`` (tested);
+        this is how BASELINE config 4 (1B edges, H = 256) is set up on 8 x 180 GB."""
+        self = cls.__new__(cls)
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        U, P = cg.num_users, cg.num_posts
+        self.num_users, self.num_posts = U, P
+        self.cu, self.cp = chunk_of(U, self.world), chunk_of(P, self.world)
+        self.u0, self.p0 = self.rank * self.cu, self.rank * self.cp
+        self.u1, self.p1 = min(self.u0 + self.cu, U), min(self.p0 + self.cp, P)
+        self.x_local = {}
+        for t, (a, b, c) in (("user", (self.u0, self.u1, self.cu)), ("post", (self.p0, self.p1, self.cp))):
+            xl = torch.zeros(c, cg.feat, dtype=dtype, device=device)
+            if b > a:
+                xl[:b - a] = cg.features(t, a, b, device, dtype)
+            self.x_local[t] = xl
+
+        def stream(rel, keep):
+            """Concatenate ``keep(edge chunk)`` over the whole edge stream of ``rel``."""
+            parts = []
+            for a in range(0, cg.n_edges(rel), chunk):
+                parts.append(keep(cg.edges(rel, a, min(a + chunk, cg.n_edges(rel)), device)))
+            if not parts:
+                return torch.empty(2, 0, dtype=torch.int64, device=device)
+            return torch.cat(parts, dim=1).contiguous()
+
+        def by_dst(a, b):
+            return lambda ei: torch.stack([ei[0], ei[1] - a])[:, (ei[1] >= a) & (ei[1] < b)]
+
+        self.rels, self.n_local_edges = {}, {}
+        n_u_pad, n_p_pad = self.cu * self.world, self.cp * self.world
+        if self.world > 1:
+            # post -> user partitioned by SOURCE post (see __init__); global in-degree of the owned users
+            deg = torch.zeros(self.cu, dtype=torch.int64, device=device)
+            parts = []
+            for a in range(0, cg.e_eng, chunk):
+                ei = cg.edges(REL_DIRECT, a, min(a + chunk, cg.e_eng), device)
+                m = (ei[0] >= self.p0) & (ei[0] < self.p1)
+                parts.append(torch.stack([ei[0] - self.p0, ei[1]])[:, m])
+                own = ei[1][(ei[1] >= self.u0) & (ei[1] < self.u1)] - self.u0
+                deg += torch.bincount(own, minlength=self.cu)
+            loc = torch.cat(parts, dim=1).contiguous() if parts else torch.empty(2, 0, dtype=torch.int64, device=device)
+            inv = 1.0 / deg.clamp(min=1).float()
+            self.rels[REL_DIRECT] = PushRelation(RelationGraph(loc, self.cp, n_u_pad), inv)
+        else:
+            loc = stream(REL_DIRECT, by_dst(self.u0, self.u1))
+            self.rels[REL_DIRECT] = RelationGraph(loc, n_p_pad, self.cu)
+        self.n_local_edges[REL_DIRECT] = int(loc.size(1))
+        loc = stream(REL_SOCIAL, by_dst(self.u0, self.u1))
+        self.rels[REL_SOCIAL] = RelationGraph(loc, n_u_pad, self.cu)
+        self.n_local_edges[REL_SOCIAL] = int(loc.size(1))
+        loc = stream(REL_ENGAGE, by_dst(self.p0, self.p1))
+        self.rels[REL_ENGAGE] = RelationGraph(loc, n_u_pad, self.cp)
+        self.n_local_edges[REL_ENGAGE] = int(loc.size(1))
+        # loss: positives = the engagement edges, evaluated by the owner of the post -> exactly the local
+        # engages edges (same filter, same order): (global user, local post)
+        self.pos_local = loc
+        self.pos_mask = None                       # a full-length mask is never built here
+        self.n_pos_global = cg.e_eng
+        self.pos_u_global = torch.cat([cg.edges(REL_ENGAGE, a, min(a + chunk, cg.e_eng), device)[0]
+                                       for a in range(0, cg.e_eng, chunk)]).contiguous() if cg.e_eng else \
+            torch.empty(0, dtype=torch.int64, device=device)
+        w = cg.post_weight(loc[1] + self.p0)
+        wsum = torch.stack([w.sum(), torch.tensor(float(w.numel()), device=device)])
+        if self.world > 1:
+            dist.all_reduce(wsum)
+        self.wbar = (wsum[0] / wsum[1]).reshape(1).float().contiguous()
+        self._layer0_src = None
+        self._neg_gen = None
+        return self
+
+    def neg_capacity(self):
+        """Room for this rank's share of E uniformly drawn negatives: mean E/G plus 8 standard deviations of
+        the binomial count (overflow probability ~1e-15) plus slack."""
+        import math
+        mean = self.n_pos_global / self.world
+        return int(min(self.n_pos_global, mean + 8.0 * math.sqrt(max(mean, 1.0)) + 1024))
+
+    def select_negatives(self, neg_p_global, capacity=None):
+        """``local_negatives`` without a host synchronisation (``trg_select_range``): the pairs
+        (pos_u[e], neg_p[e] - p0) with neg_p[e] owned here, in edge order, padded to ``capacity`` entries with the
+        sentinel pair (n_users_padded, posts_per_rank) that CSR builds with one extra row absorb.  The count
+        never travels to the host, so the CPU keeps enqueueing ahead of the GPU; more than ``capacity`` local
+        negatives (a caller whose negatives are far from ``torch.randint``'s uniform draw, train_gnn.py:272)
+        abort the kernel with a message -- pass ``capacity=E`` or use ``local_negatives`` for such inputs."""
+        from . import _lib
+        lib = _lib.load()
+        e = self.n_pos_global
+        if neg_p_global.dtype != torch.int64 or neg_p_global.numel() != e:
+            raise _lib.TrgError("neg_p must be int64 with one entry per positive edge (train_gnn.py:272)")
+        cap = int(self.neg_capacity() if capacity is None else capacity)
+        dev = self.pos_u_global.device
+        user = torch.empty(cap, dtype=torch.int64, device=dev)
+        post = torch.empty(cap, dtype=torch.int64, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.trg_select_range_workspace_bytes(e))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.call("trg_select_range", e * 16 + cap * 32, lib.trg_select_range, _lib.ptr(neg_p_global.contiguous()),
+                  _lib.ptr(self.pos_u_global), e, self.p0, self.p1, cap, self.cp, self.cu * self.world,
+                  _lib.ptr(post), _lib.ptr(user), _lib.ptr(count), _lib.ptr(ws), ws_bytes, _lib.stream())
+        return PaddedPairs(user, post, count)
+
     def layer0_sources(self):
         """Input features are static: gather them once (train_gnn.py:211 moves the graph once)."""
         if self._layer0_src is None:
             self._layer0_src = {"user": _all_gather_rows(self.x_local["user"]), "post": self.x_local["post"]}
         return self._layer0_src
+
+
+class PaddedPairs:
+    """(global user, local post) pairs of this rank's negatives padded to a fixed capacity with sentinel ids
+    (``ShardedGraph.select_negatives``); ``count`` is a device int32 -- nothing here is known on the host."""
+
+    def __init__(self, user, post, count):
+        self.user, self.post, self.count = user, post, count
 
 
 def forward_sharded(model, shard: ShardedGraph, ops=CUDA_OPS):

@@ -23,7 +23,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from .dist import ShardedGraph, allreduce_grads
+from .dist import PaddedPairs, ShardedGraph, allreduce_grads
 from .graph import PushRelation
 from .nn import REL_DIRECT, REL_ENGAGE, REL_SOCIAL, StackedWeightedRGCN, WeightedRGCN
 
@@ -103,9 +103,17 @@ class CudaStepPrims:
         return sage_proj_bwd_input(dz, terms)
 
     @staticmethod
-    def csr(other, key, n_key, n_other, per_step=False):
+    def csr(other, key, n_key, n_other, per_step=False, sentinel=False):
+        """``sentinel``: the pairs are padded with key = n_key (PaddedPairs); the structure is built with one
+        extra row that collects the padding and is never visited (consumers walk rows [0, n_key))."""
         from .graph import build_csr
-        return build_csr(other, key, n_key, n_other, validate=False, per_step=per_step)
+        c = build_csr(other, key, n_key + (1 if sentinel else 0), n_other, validate=False, per_step=per_step)
+        c.n_rows = n_key
+        return c
+
+    @staticmethod
+    def select_negatives(shard, neg_p_global, capacity=None):
+        return shard.select_negatives(neg_p_global, capacity)
 
     @staticmethod
     def anchor_loss(csr, anchor, gathered, n_edges, label, wbar, g_anchor, relu_gate, coef_in_csr_order=False):
@@ -149,10 +157,13 @@ def eligible(model, shard: ShardedGraph) -> bool:
 
 
 @torch.no_grad()
-def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_STEP_PRIMS, neg_ready=None):
+def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_STEP_PRIMS, neg_ready=None,
+                           neg_p_global=None, neg_capacity=None):
     """Forward + link loss + backward on this rank's partition.  Returns the LOCAL partial loss
     (0-d); local parameter-gradient partials are accumulated into ``.grad`` (the caller all-reduces
-    both).  ``neg_p_local``: ``shard.local_negatives(neg_p)``."""
+    both).  Negatives: ``neg_p_local`` = ``shard.local_negatives(neg_p)`` (or a ``PaddedPairs``), or
+    ``neg_p_global`` = the step's full ``neg_p`` -- this rank's share is then selected here, on the device
+    and without a host sync, while the final user rows are being all-gathered."""
     layers = list(model.layers) if type(model) is StackedWeightedRGCN else [model]
     prel_d, rel_s, rel_e = shard.rels[REL_DIRECT], shard.rels[REL_SOCIAL], shard.rels[REL_ENGAGE]
     rel_d = prel_d.rel                                  # rows ("fwd") = all users, sources = local posts
@@ -191,8 +202,13 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     st = shard.loss_structures(prims)
     if neg_ready is not None:          # host negatives: their copy ran on a side stream during the forward
         torch.cuda.current_stream().wait_event(neg_ready)
-    neg_by_post = prims.csr(neg_p_local[0], neg_p_local[1], shard.cp, n_u_pad, per_step=True)      # || all-gather
-    neg_by_user = prims.csr(neg_p_local[1], neg_p_local[0], n_u_pad, shard.cp, per_step=True)
+    if neg_p_local is None:
+        neg_p_local = prims.select_negatives(shard, neg_p_global, neg_capacity)                    # || all-gather
+    padded = isinstance(neg_p_local, PaddedPairs)
+    neg_u, neg_pl = (neg_p_local.user, neg_p_local.post) if padded else (neg_p_local[0], neg_p_local[1])
+    kw = {"sentinel": True} if padded else {}
+    neg_by_post = prims.csr(neg_u, neg_pl, shard.cp, n_u_pad, per_step=True, **kw)                  # || all-gather
+    neg_by_user = prims.csr(neg_pl, neg_u, n_u_pad, shard.cp, per_step=True, **kw)
     user_full = ag.wait()
     e_glob = shard.n_pos_global
     seq = "pos_by_user_p" in st     # positives: coefficients written in by-post order (static remap)
@@ -250,19 +266,29 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
 
 
 def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global=None, neg_p_local=None,
-                             prims=CUDA_STEP_PRIMS, return_tensor=False):
-    """``dist.train_step_sharded`` without the tape and with the collectives overlapped."""
+                             prims=CUDA_STEP_PRIMS, return_tensor=False, neg_capacity=None):
+    """``dist.train_step_sharded`` without the tape and with the collectives overlapped.
+
+    ``neg_p_global``: the step's ``torch.randint(0, P, (E,))`` (train_gnn.py:272) -- the SAME array on every
+    rank, device or (pinned) host; ``None`` draws it from the shard's rank-synchronised generator.  Each rank
+    keeps the pairs whose negative post it owns; that selection runs on the device inside the step with no
+    host synchronisation (``ShardedGraph.select_negatives``; ``neg_capacity`` overrides its room).
+    ``neg_p_local``: a share already selected by the caller (``shard.local_negatives``)."""
     model.train()
     optimizer.zero_grad()
+    is_cuda = shard.x_local["user"].is_cuda
+    neg_ready = None
     if neg_p_local is None:
         if neg_p_global is None:
             neg_p_global = shard.draw_negatives()          # rank-synchronised generator: same array everywhere
-        neg_p_local = shard.local_negatives(neg_p_global)
-    neg_ready = None
-    if not neg_p_local.is_cuda and shard.x_local["user"].is_cuda:
+        if not neg_p_global.is_cuda and is_cuda:
+            from .train import stage_negatives
+            neg_p_global, neg_ready = stage_negatives(neg_p_global, shard.x_local["user"].device)
+    elif torch.is_tensor(neg_p_local) and not neg_p_local.is_cuda and is_cuda:
         from .train import stage_negatives
         neg_p_local, neg_ready = stage_negatives(neg_p_local, shard.x_local["user"].device)
-    loss = loss_and_grads_sharded(model, shard, neg_p_local, prims, neg_ready=neg_ready).clone()
+    loss = loss_and_grads_sharded(model, shard, neg_p_local, prims, neg_ready=neg_ready, neg_p_global=neg_p_global,
+                                  neg_capacity=neg_capacity).clone()
     lw = dist.all_reduce(loss, async_op=True)
     allreduce_grads(list(model.parameters()))
     optimizer.step()

@@ -112,3 +112,89 @@ def init_state_dict(hidden, feat, num_layers=1, seed=1):
             sd[f"{pre}{conv}.lin_l.bias"] = lin_l.bias.detach().clone()
             sd[f"{pre}{conv}.lin_r.weight"] = lin_r.weight.detach().clone()
     return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# counter-based graphs: every edge / feature row is a pure function of its index
+# ------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _i64(x: int) -> int:
+    """Python int -> the int64 with the same low 64 bits (torch int64 arithmetic wraps)."""
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr(x: torch.Tensor, k: int) -> torch.Tensor:
+    """Logical right shift of int64 (``>>`` on a signed tensor is arithmetic)."""
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def hash64(idx: torch.Tensor, salt: int) -> torch.Tensor:
+    """splitmix64 finaliser of ``idx + salt * golden``: a counter-based generator -- element i of a stream
+    depends on i alone, so any rank can produce any slice of it without producing the rest."""
+    z = idx + _i64(0x9E3779B97F4A7C15 * (2 * salt + 1))
+    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+class CounterGraph:
+    """A synthetic user-post graph of the SynthGraph family whose parts can be generated independently:
+    edge e of a relation is ``(hash(e, a) mod N_src, hash(e, b) mod N_dst)`` (uniform endpoints, duplicates
+    kept), feature rows come in fixed blocks of ``ROW_BLOCK`` rows each seeded by its block id, and the
+    interaction weight of a post is a hash of its id.  BASELINE config 4 (1B edges, H = 256: 30 GB of
+    features and 16 GB of COO) cannot round-trip through one host or one GPU; with this
+    generator every rank produces exactly the rows and edges it owns, on its own device
+    (``dist.ShardedGraph.from_generator``).  ``materialize`` builds the whole graph for sizes where that is
+    possible -- the tests compare the sharded-from-generator path with it."""
+
+    ROW_BLOCK = 1 << 16
+
+    def __init__(self, num_users, num_posts, e_eng, e_soc, feat, seed=0):
+        self.num_users, self.num_posts = int(num_users), int(num_posts)
+        self.e_eng, self.e_soc, self.feat, self.seed = int(e_eng), int(e_soc), int(feat), int(seed)
+
+    def n_edges(self, rel):
+        return self.e_soc if rel == REL_SOCIAL else self.e_eng
+
+    def edges(self, rel, a, b, device):
+        """``edge_index[:, a:b]`` of relation ``rel`` (int64 ``[2, b - a]``)."""
+        e = torch.arange(a, b, device=device, dtype=torch.int64)
+        s0 = 16 * self.seed
+        if rel == REL_SOCIAL:
+            return torch.stack([_lsr(hash64(e, s0 + 3), 1) % self.num_users,
+                                _lsr(hash64(e, s0 + 4), 1) % self.num_users])
+        u = _lsr(hash64(e, s0 + 1), 1) % self.num_users
+        p = _lsr(hash64(e, s0 + 2), 1) % self.num_posts
+        return torch.stack([u, p]) if rel == REL_ENGAGE else torch.stack([p, u])
+
+    def features(self, node_type, r0, r1, device, dtype=torch.float32):
+        """Unit-norm rows ``[r0, r1)`` of a node type's feature table (build_graph.py:452-456 normalises rows)."""
+        if r1 <= r0:
+            return torch.empty(0, self.feat, device=device, dtype=dtype)
+        rb = self.ROW_BLOCK
+        out = []
+        for blk in range(r0 // rb, (r1 - 1) // rb + 1):
+            g = torch.Generator(device=device).manual_seed(
+                (self.seed * 1_000_003 + (0 if node_type == "user" else 500_000_000) + blk) & 0x7FFFFFFFFFFFFFFF)
+            x = F.normalize(torch.randn(rb, self.feat, generator=g, device=device), dim=1)
+            lo, hi = max(r0, blk * rb) - blk * rb, min(r1, (blk + 1) * rb) - blk * rb
+            out.append(x[lo:hi].to(dtype))
+        return torch.cat(out) if len(out) > 1 else out[0]
+
+    def post_weight(self, post_ids):
+        """interaction-type weight of posts (train_gnn.py:226-237): 3.0 ("QT") with probability 1/4, else 1.0."""
+        h = _lsr(hash64(post_ids, 16 * self.seed + 5), 1) % 4
+        return torch.where(h == 0, 3.0, 1.0).float()
+
+    def materialize(self, device="cpu", dtype=torch.float32) -> SynthGraph:
+        eng = self.edges(REL_ENGAGE, 0, self.e_eng, device)
+        soc = self.edges(REL_SOCIAL, 0, self.e_soc, device)
+        w = torch.zeros(self.num_users + self.num_posts, device=device)
+        w[self.num_users:] = self.post_weight(torch.arange(self.num_posts, device=device))
+        ei = {REL_SOCIAL: soc, REL_ENGAGE: eng, REL_DIRECT: eng.flip(0).contiguous()}
+        x = {"user": self.features("user", 0, self.num_users, device, dtype),
+             "post": self.features("post", 0, self.num_posts, device, dtype)}
+        return SynthGraph(x, ei, eng, w, self.num_users, self.num_posts)
