@@ -7,7 +7,7 @@ import truth_recommendation_gnn_b200 as trg
 from oracle import sage as osage
 from oracle import topk as otopk
 from tests.util import (TOL_BF16, TOL_F32, assert_as_accurate_as_fp32, assert_close, assert_close_elementwise,
-                        golden_graph, load_golden, oracle_model)
+                        golden_graph, load_golden, oracle_grads_with_gates, oracle_model, product_gates)
 from truth_recommendation_gnn_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -178,25 +178,12 @@ def test_fused_step_matches_autograd_and_oracle(dev, layers, h, dtype, tol):
     sd = synth.init_state_dict(h, h, layers)
     rnd = (lambda t: t.to(dtype).float())
     neg = synth.synth_neg(P, Ee, 2)
-    # ReLU is discontinuous: a pre-activation within rounding of 0 can be gated either way by two correct fp32
-    # implementations.  The test input is chosen by a property of the ORACLE alone (fp64 run): the first seeded
-    # graph whose smallest |pre-activation| is > 1e-6 of the layer's scale -- nothing about the code under test
-    # enters the choice.
-    for seed in range(11, 19):
-        g = synth.synth_graph(U, P, Ee, Es, h, seed=seed, skew=True)
-        xr = {k: rnd(v) for k, v in g.x_dict.items()}
-        m64 = oracle_model(h, layers, {k: rnd(v) for k, v in sd.items()}).double()
-        x64 = {k: v.double() for k, v in xr.items()}
-        if osage.relu_margin(m64, x64, g.edge_index_dict) > 1e-6:
-            break
-    else:
-        raise AssertionError("no seeded graph with a ReLU margin above fp32 rounding")
-    ref = oracle_model(h, layers, {k: rnd(v) for k, v in sd.items()})
+    g = synth.synth_graph(U, P, Ee, Es, h, seed=11, skew=True)
+    xr = {k: rnd(v) for k, v in g.x_dict.items()}
+    sdr = {k: rnd(v) for k, v in sd.items()}
+    ref = oracle_model(h, layers, sdr)
     gd = g.to(dev)
     xd = {k: v.to(dtype) for k, v in gd.x_dict.items()}
-    o64 = m64(x64, g.edge_index_dict)
-    osage.link_loss(o64["user"], o64["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
-                    g.interaction_type_tensor.double(), U).backward()
     out = ref(xr, g.edge_index_dict)
     l_ref = osage.link_loss(out["user"], out["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
                             g.interaction_type_tensor, U)
@@ -211,13 +198,18 @@ def test_fused_step_matches_autograd_and_oracle(dev, layers, h, dtype, tol):
     assert torch.equal(l_fused, l_auto.detach())              # same forward kernels, same inputs
     ltol = TOL_F32 if dtype == torch.float32 else TOL_BF16
     assert abs(float(l_fused) - float(l_ref)) <= ltol * abs(float(l_ref))
+    g_gated = None
+    if dtype == torch.float32:
+        g_copy = synth.SynthGraph(xr, g.edge_index_dict, g.train_edge_index, g.interaction_type_tensor, U, P)
+        _, g_gated, _ = oracle_grads_with_gates(h, layers, sdr, g_copy, neg, product_gates(m_auto, xd, gd.edge_index_dict))
     for (n, a), (_, b), (_, r) in zip(m_fused.named_parameters(), m_auto.named_parameters(), ref.named_parameters()):
         assert a.grad is not None and a.grad.dtype == a.dtype, n
         assert_close(a.grad.float().cpu(), b.grad.float().cpu(), tol, f"fused vs autograd grad {n}")
-        g64 = dict(m64.named_parameters())[n].grad
         if dtype == torch.float32:
-            # as close to the fp64 oracle as the reference's own fp32 arithmetic (the fp32 CPU oracle) is
-            assert_as_accurate_as_fp32(a.grad.cpu(), r.grad, g64, tol, f"fused vs oracle grad {n}")
+            # ReLU gates within rounding of 0 may be decided either way (oracle.sage.forward_gated): the
+            # oracle's gradients are taken with the gates the product applied, after checking (fp64) that
+            # those differ from the exact gates only at the kink.  No seed search, no slack.
+            assert_close(a.grad.cpu(), g_gated[n], tol, f"fused vs oracle grad {n}")
         elif layers == 1 or n.startswith(f"layers.{layers - 1}."):
             # bf16 stores every intermediate gradient table in bf16 and flips ReLU gates near 0: deeper
             # layers are only checked against the tape path (same storage), the last layer against the oracle
@@ -435,5 +427,10 @@ def test_cfg1_full_size_against_oracle(dev):
         l_gpu = trg.train_step(model, torch.optim.Adam(model.parameters(), lr=1e-3), gd.x_dict, gd.edge_index_dict,
                                gd.train_edge_index, gd.interaction_type_tensor, U, P, neg_p=neg.to(dev))
         assert abs(l_gpu - l_ref) <= TOL_F32 * abs(l_ref), (L, l_gpu, l_ref)
-        for (n, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
-            assert_close(a.grad.cpu(), b.grad, 5 * TOL_F32, f"cfg1 L={L} grad {n}")
+        # 3.8M ReLU inputs per layer: some pre-activation is always within fp32 rounding of 0, and one gate
+        # decided the other way moves a gradient by ~1e-3 -- compare given the product's gates (checked
+        # against the fp64 oracle to differ only at the kink; oracle.sage.forward_gated)
+        probe = _gpu_model(H, L, sd, dev)
+        _, g_gated, n_amb = oracle_grads_with_gates(H, L, sd, g, neg, product_gates(probe, gd.x_dict, gd.edge_index_dict))
+        for n, a in model.named_parameters():
+            assert_close(a.grad.cpu(), g_gated[n], 5 * TOL_F32, f"cfg1 L={L} grad {n} ({n_amb} ambiguous gates)")

@@ -79,3 +79,41 @@ def assert_as_accurate_as_fp32(a, b32, b64, tol, what="", floor_frac=1e-3, slack
     assert e_a <= max(tol, slack * e_ref), (f"{what}: element-wise err vs fp64 oracle {e_a:.3e} > max({tol:.1e}, "
                                             f"{slack} x fp32-oracle err {e_ref:.3e})")
     return e_a, e_ref
+
+
+def product_gates(model, x_dict, edge_index_dict):
+    """ReLU gates the product applied, layer by layer (``out > 0`` of every block), as CPU bool masks."""
+    layers = list(model.layers) if hasattr(model, "layers") else [model]
+    gates, x = [], x_dict
+    with torch.no_grad():
+        for layer in layers:
+            x = layer(x, edge_index_dict)
+            gates.append({k: (v > 0).cpu() for k, v in x.items()})
+    return gates
+
+
+def oracle_grads_with_gates(h, layers, sd, g, neg, gates, dtype=torch.float32, kink=1e-5):
+    """Gradients of the reference loss (train_gnn.py:259-283) from the oracle with the ReLU gates forced to
+    ``gates`` (see ``oracle.sage.forward_gated``), after checking against an fp64 run that those gates differ
+    from the exact ones ONLY where the pre-activation is within ``kink`` (relative to the layer's scale) of 0.
+    Returns ``(loss, {param name: grad}, n_ambiguous_gates)``."""
+    m64 = oracle_model(h, layers, sd).double()
+    x64 = {k: v.double() for k, v in g.x_dict.items()}
+    with torch.no_grad():
+        _, zs = osage.forward_gated(m64, x64, g.edge_index_dict, gates)
+    n_amb = 0
+    for l, (z_u, z_p) in enumerate(zs):
+        for z, gate, what in ((z_u, gates[l]["user"], "user"), (z_p, gates[l]["post"], "post")):
+            if not z.numel():
+                continue
+            wrong = gate != (z > 0)
+            if bool(wrong.any()):
+                worst = float(z[wrong].abs().max() / z.abs().max())
+                assert worst <= kink, f"layer {l} {what}: a gate differs where |z| = {worst:.2e} of the scale"
+                n_amb += int(wrong.sum())
+    m = oracle_model(h, layers, sd).to(dtype)
+    out, _ = osage.forward_gated(m, {k: v.to(dtype) for k, v in g.x_dict.items()}, g.edge_index_dict, gates)
+    loss = osage.link_loss(out["user"], out["post"], g.train_edge_index[0], g.train_edge_index[1], neg,
+                           g.interaction_type_tensor.to(dtype), g.num_users)
+    loss.backward()
+    return float(loss), {n: p.grad for n, p in m.named_parameters()}, n_amb
