@@ -477,20 +477,29 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     r = gpu_train_bench(args, w, rank, world, dev, args.steps, args.warmup)
-    extras = {}
+    extras, errors = {}, {}
+
+    def leg(name, fn):
+        # a secondary leg that fails must not take the headline line with it: the error is reported in its place
+        try:
+            extras[name] = fn()
+        except Exception as e:      # noqa: BLE001
+            errors[name] = f"{type(e).__name__}: {e}"[:400]
+            torch.cuda.empty_cache()
+
     if not args.no_extras and default_workload:
         sub_steps = min(args.steps, 10)
         if world > 1:
             from truth_recommendation_gnn_b200 import dist_check
-            extras["verify"] = [dist_check.check_sharded_against_single(dev, dt) for dt in (torch.float32, torch.bfloat16)]
+            leg("verify", lambda: [dist_check.check_sharded_against_single(dev, dt) for dt in (torch.float32, torch.bfloat16)])
         w3 = WORKLOADS["cfg3"]
-        extras["cfg3"] = (w3, gpu_train_bench(args, w3, rank, world, dev, sub_steps, 3, e2e=False), sub_steps)
+        leg("cfg3", lambda: (w3, gpu_train_bench(args, w3, rank, world, dev, sub_steps, 3, e2e=False), sub_steps))
         if world == 8:
             w4 = WORKLOADS["cfg4"]
-            extras["cfg4"] = (w4, gpu_train_bench(args, w4, rank, world, dev, min(args.steps, 5), 3, e2e=False), min(args.steps, 5))
-    topk = None
+            leg("cfg4", lambda: (w4, gpu_train_bench(args, w4, rank, world, dev, min(args.steps, 5), 3, e2e=False), min(args.steps, 5)))
     if not args.no_topk:
-        topk = gpu_topk_bench(dev, rank, world)
+        leg("topk", lambda: gpu_topk_bench(dev, rank, world))
+    topk = extras.get("topk")
 
     if rank == 0:
         pk = peaks()
@@ -543,6 +552,8 @@ def main():
                 line[name] = sub_line(name, wk, rk, world, st)
         if topk is not None:
             line["topk"] = topk
+        if errors:
+            line["leg_errors"] = errors
         if world == 1 and not args.no_extras and default_workload:
             line["cfg1"] = gpu_cfg1(dev)
         if not args.no_cpu_baseline and world == 1:
