@@ -477,12 +477,20 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     r = gpu_train_bench(args, w, rank, world, dev, args.steps, args.warmup)
+    if rank == 0:
+        print(f"[bench] headline {args.workload} x{world}: {r['ms']:.3f} ms/step, e2e {r['ms_e2e']:.3f}, "
+              f"kernels {({k: round(v['ms'] / args.steps, 3) for k, v in sorted(r['prof'].items())})}",
+              file=sys.stderr, flush=True)
     extras, errors = {}, {}
 
     def leg(name, fn):
         # a secondary leg that fails must not take the headline line with it: the error is reported in its place
         try:
             extras[name] = fn()
+            if rank == 0:           # progress on stderr: a later leg that kills the job does not erase this one
+                v = extras[name]
+                ms = v[1]["ms"] if isinstance(v, tuple) else (v.get("ms_per_batch") if isinstance(v, dict) else None)
+                print(f"[bench] leg {name} done" + (f": {ms:.3f} ms" if ms else ""), file=sys.stderr, flush=True)
         except Exception as e:      # noqa: BLE001
             errors[name] = f"{type(e).__name__}: {e}"[:400]
             torch.cuda.empty_cache()

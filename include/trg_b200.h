@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TRG_ABI_VERSION 3
+#define TRG_ABI_VERSION 4
 
 enum { TRG_F32 = 0, TRG_BF16 = 1 };
 enum {
@@ -130,6 +130,21 @@ int trg_gather_wsum(const int32_t* rowptr, const int32_t* col, const int32_t* ei
  * the arithmetic is fp32 and out is rounded to dtype once.  out may alias add. */
 int trg_rows_finish(const void* in, int in_dtype, const float* row_scale, const void* add,
                     const void* relu_of, int64_t n_rows, int32_t feat, int dtype, void* out, void* stream);
+
+/* ---- reduce-scatter FUSED with the row finish, over peer memory (multi-GPU only) ----------------
+ *     out[r, :] = gate( row_scale[r] * sum_{g < n_peers} parts[g][row0 + r, :] + add[r, :] )
+ * parts: HOST array of n_peers DEVICE pointers, one per rank in rank order, each the base of that rank's
+ * full-height [>= row0 + n_rows, feat] table of partial sums (in_dtype: TRG_F32 or dtype), all addressable
+ * from this device (cudaIpc / CUDA VMM peer mappings over NVLink; parts[own rank] is local memory).  The
+ * caller owns the cross-rank ordering: every rank's table is complete before the call (a barrier on the
+ * stream) and is not overwritten until every peer's call has finished.  The sum runs in rank order
+ * (deterministic); row_scale / add / relu_of as in trg_rows_finish.  Replaces an NCCL reduce-scatter plus
+ * trg_rows_finish: the rows cross NVLink inside the kernel's own loads and the reduced table is never
+ * materialised.  ctas_per_sm (0 = default 2): CTAs of 256 threads per SM -- the kernel is latency-bound on
+ * the links and is meant to run beside a compute kernel. */
+int trg_peer_reduce_rows(const void* const* parts, int32_t n_peers, int64_t row0, int in_dtype,
+                         const float* row_scale, const void* add, const void* relu_of, int64_t n_rows,
+                         int32_t feat, int dtype, void* out, int32_t ctas_per_sm, void* stream);
 
 /* ---- A5+A6 / K4: fused positive/negative edge score + BCE-with-logits -------------------------
  * Replaces train_gnn.py:259-281:  pos = <u[pos_u], p[pos_p]>, neg = <u[pos_u], p[neg_p]>,

@@ -495,6 +495,43 @@ def test_rows_finish(dev, dtype, in_f32):
     assert Fn.rows_finish(xd[:0], dtype).shape == (0, f)
 
 
+@pytest.mark.parametrize("dtype,in_f32", [(torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)])
+@pytest.mark.parametrize("n_peers", [1, 2, 3, 8])
+def test_peer_reduce_rows(dev, dtype, in_f32, n_peers):
+    """trg_peer_reduce_rows = reduce-scatter + trg_rows_finish in one kernel: the owned row range of G partial
+    tables summed in rank order (bit-equal to the sequential fp32 sum), then 1/deg, local term, ReLU gate, one
+    rounding.  The G tables live on this device here; over NVLink they are the peers' mapped buffers."""
+    gen = torch.Generator().manual_seed(7 + n_peers)
+    rows, f, row0, n = 900, 128, 300, 500
+    parts = [torch.randn(rows, f, generator=gen) for _ in range(n_peers)]
+    if not in_f32:
+        parts = [p.bfloat16().float() for p in parts]
+    add = torch.randn(n, f, generator=gen).to(dtype).float()
+    act = torch.relu(torch.randn(n, f, generator=gen)).to(dtype).float()
+    rs = torch.rand(n, generator=gen)
+    pd = [p.to(dev) if in_f32 else p.to(dev).to(dtype) for p in parts]
+    seq = parts[0][row0:row0 + n].clone()
+    for p in parts[1:]:
+        seq = seq + p[row0:row0 + n]                       # fp32, rank order
+    out = Fn.peer_reduce_rows(pd, row0, n, dtype, row_scale=rs.to(dev))
+    assert out.dtype == dtype and out.shape == (n, f)
+    exp = seq * rs[:, None]
+    if dtype == torch.float32:
+        assert torch.equal(out.cpu(), exp)
+    else:
+        assert torch.equal(out.cpu(), exp.to(dtype))
+    out = Fn.peer_reduce_rows(pd, row0, n, dtype, add=add.to(dev).to(dtype), relu_of=act.to(dev).to(dtype))
+    exp = torch.where(act > 0, seq + add, torch.zeros(()))
+    assert torch.equal(out.cpu(), exp.to(dtype))
+    # same result as the two-step form it replaces
+    two = Fn.rows_finish(torch.stack([p[row0:row0 + n].float() for p in pd]).sum(0) if n_peers > 2 else
+                         (pd[0][row0:row0 + n].float() + (pd[1][row0:row0 + n].float() if n_peers == 2 else 0)),
+                         dtype, add=add.to(dev).to(dtype), relu_of=act.to(dev).to(dtype))
+    tol = TOL_F32 if dtype == torch.float32 else 2.0 ** -7
+    assert_close(out.float().cpu(), two.float().cpu(), tol, "fused vs reduce + finish")
+    assert Fn.peer_reduce_rows(pd, 0, 0, dtype).shape == (0, f)
+
+
 def test_csr_build_aborts_on_out_of_range_per_step_ids(dev):
     """Per-step structures skip the host-side range check (no sync inside a step); K0's histogram pass then
     aborts the kernel on an id outside [0, n_key) instead of corrupting memory.  The abort poisons the CUDA

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtrg_b200.so")
 
 TRG_F32, TRG_BF16 = 0, 1
-ABI_VERSION = 3    # TRG_ABI_VERSION of include/trg_b200.h
+ABI_VERSION = 4    # TRG_ABI_VERSION of include/trg_b200.h
 
 _vp, _i64, _i32, _sz, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t, ctypes.c_int
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     "trg_gather_wsum": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _int, _vp, _int, _int, _vp,
                                ctypes.POINTER(TrgLongRows), _vp]),
     "trg_rows_finish": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i32, _int, _vp, _vp]),
+    "trg_peer_reduce_rows": (_int, [_vp, _i32, _i64, _int, _vp, _vp, _vp, _i64, _i32, _int, _vp, _i32, _vp]),
     "trg_edge_bce_workspace_bytes": (_sz, [_i64]),
     "trg_edge_bce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _int, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -191,7 +191,14 @@ class ShardedGraph:
         """Room for this rank's share of E uniformly drawn negatives: mean E/G plus 8 standard deviations of
         the binomial count (overflow probability ~1e-15) plus slack."""
         import math
-        mean = self.n_pos_global / self.world
+        # torch.randint (train_gnn.py:272) maps a 32-bit draw with `% P` when P < 2^32: the low
+        # (2^32 mod P) values come up floor(2^32 / P) + 1 times in 2^32, the rest floor(2^32 / P) times.
+        # At P = 50M that is a +1.2 % share for the low ids -- more than 8 sigma of a 100M-entry share --
+        # so the bound uses the largest per-value probability, not 1 / P.
+        p_max = 1.0 / self.num_posts
+        if self.num_posts < 2**32:
+            p_max = (2**32 // self.num_posts + 1) / 2.0**32
+        mean = self.n_pos_global * min(1.0, self.cp * p_max)
         return int(min(self.n_pos_global, mean + 8.0 * math.sqrt(max(mean, 1.0)) + 1024))
 
     def select_negatives(self, neg_p_global, capacity=None):

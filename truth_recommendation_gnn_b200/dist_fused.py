@@ -65,6 +65,69 @@ def reduce_scatter_rows_async(g_full: torch.Tensor) -> _Pending:
     return _Pending(dist.reduce_scatter_tensor(out, g_full, op=dist.ReduceOp.SUM, async_op=True), out, keep=g_full)
 
 
+class _Finished:
+    """A reduce-scatter in flight whose owned rows are finished (1/deg, local term, ReLU backward) by a
+    separate pass on the consumer's stream when they are first needed."""
+
+    def __init__(self, pending, finish):
+        self.pending, self.finish = pending, finish
+
+    def wait(self):
+        return self.finish(self.pending.wait())
+
+
+class LibraryComm:
+    """The bandwidth collectives as ``torch.distributed`` calls (NCCL kernels on the GPU box -- the A/B of the
+    peer-memory path --, gloo in the CPU tests of this host logic)."""
+
+    def all_gather_rows_async(self, x_local):
+        return all_gather_rows_async(x_local)
+
+    def partial(self, rows, feat, dtype):
+        return None                                    # the producing kernel allocates its own table
+
+    def reduce_finish_async(self, part, dtype, prims, row_scale=None, add=None, relu_of=None):
+        return _Finished(reduce_scatter_rows_async(part),
+                         lambda t: prims.rows_finish(t, dtype, row_scale=row_scale, add=add, relu_of=relu_of))
+
+
+class PeerMemoryComm:
+    """The bandwidth collectives over peer memory (``peer.PeerComm``): copy-engine all-gather, and the
+    reduce-scatter fused with the row finish in ``trg_peer_reduce_rows``."""
+
+    def __init__(self, pc):
+        self.pc = pc
+
+    def all_gather_rows_async(self, x_local):
+        return self.pc.all_gather_rows_async(x_local)
+
+    def partial(self, rows, feat, dtype):
+        return self.pc.acquire_partial(rows, feat, dtype)
+
+    def reduce_finish_async(self, part, dtype, prims, row_scale=None, add=None, relu_of=None):
+        return self.pc.reduce_rows_async(part, dtype, row_scale=row_scale, add=add, relu_of=relu_of)
+
+
+LIBRARY_COMM = LibraryComm()
+
+
+def comm_for(model, shard: ShardedGraph):
+    """Peer-memory collectives for CUDA shards whose ranks can map each other's memory (one NVLink / NVSwitch
+    node); ``TRG_DIST_COMM=nccl`` keeps the library collectives (A/B).  The choice is made once per shard."""
+    c = getattr(shard, "_comm", None)
+    if c is not None:
+        return c
+    x = shard.x_local["user"]
+    c = LIBRARY_COMM
+    import os
+    if x.is_cuda and dist.get_backend() == "nccl" and os.environ.get("TRG_DIST_COMM", "peer") != "nccl":
+        from .peer import peer_comm_for
+        feat = max([x.size(1), shard.x_local["post"].size(1)] + [int(p.size(0)) for p in model.parameters() if p.dim() == 2])
+        c = PeerMemoryComm(peer_comm_for(shard, feat, x.dtype, transport_dtype(x.dtype)))
+    shard._comm = c
+    return c
+
+
 # ------------------------------------------------------------------------------------------
 # compute primitives (CUDA)
 # ------------------------------------------------------------------------------------------
@@ -158,7 +221,7 @@ def eligible(model, shard: ShardedGraph) -> bool:
 
 @torch.no_grad()
 def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_STEP_PRIMS, neg_ready=None,
-                           neg_p_global=None, neg_capacity=None):
+                           neg_p_global=None, neg_capacity=None, comm=None):
     """Forward + link loss + backward on this rank's partition.  Returns the LOCAL partial loss
     (0-d); local parameter-gradient partials are accumulated into ``.grad`` (the caller all-reduces
     both).  Negatives: ``neg_p_local`` = ``shard.local_negatives(neg_p)`` (or a ``PaddedPairs``), or
@@ -171,6 +234,8 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     n_u_pad = shard.cu * shard.world
     dtype = hu.dtype
     xfer = transport_dtype(dtype)
+    pdt = xfer or dtype                                 # element type of the partial-sum tables
+    comm = comm or LIBRARY_COMM
 
     # ---- forward ----
     saved = []
@@ -180,16 +245,17 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
             conv.lin_l.materialize(xs.size(-1))
             conv.lin_r.materialize(xd.size(-1))
         wd, ws = float(layer.w_direct), float(layer.w_social)
-        ag = None if i == 0 else all_gather_rows_async(hu)
-        part = prims.gather_sum(rel_d, "fwd", hp, out_dtype=xfer)       # [U_pad, F] partial sums  || all-gather
-        rs = reduce_scatter_rows_async(part)
+        ag = None if i == 0 else comm.all_gather_rows_async(hu)
+        part = prims.gather_sum(rel_d, "fwd", hp, out=comm.partial(n_u_pad, hp.size(1), pdt),
+                                out_dtype=xfer)                          # [U_pad, F] partial sums  || all-gather
+        rs = comm.reduce_finish_async(part, dtype, prims, row_scale=prel_d.inv_deg)   # sum / global in-degree
         del part
         user_full = shard.layer0_sources()["user"] if i == 0 else ag.wait()
         mean_s = prims.agg_mean(rel_s, user_full)                        # || reduce-scatter
         mean_e = prims.agg_mean(rel_e, user_full)
         del user_full
         hp_n = prims.proj_fwd([(mean_e, p.lin_l.weight, 1.0), (hp, p.lin_r.weight, 1.0)], p.lin_l.bias, True)
-        mean_d = prims.rows_finish(rs.wait(), hu.dtype, row_scale=prel_d.inv_deg)     # sum / global in-degree
+        mean_d = rs.wait()
         w_root = wd * d.lin_r.weight + ws * s.lin_r.weight
         b_user = wd * d.lin_l.bias + ws * s.lin_l.bias
         hu_n = prims.proj_fwd([(mean_d, d.lin_l.weight, wd), (mean_s, s.lin_l.weight, ws), (hu, w_root, 1.0)],
@@ -198,7 +264,7 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
         hu, hp = hu_n, hp_n
 
     # ---- loss: every <u, p> term is evaluated by the owner of the post (dist.ShardedGraph) ----
-    ag = all_gather_rows_async(hu)
+    ag = comm.all_gather_rows_async(hu)
     st = shard.loss_structures(prims)
     if neg_ready is not None:          # host negatives: their copy ran on a side stream during the forward
         torch.cuda.current_stream().wait_event(neg_ready)
@@ -216,9 +282,11 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
                                           **({"coef_in_csr_order": True} if seq else {}))
     l_neg, c_neg, dz_p = prims.anchor_loss(neg_by_post, hp, user_full, e_glob, 0, shard.wbar, g_p, True)
     del user_full
-    g_uf = prims.wsum(st["pos_by_user_p" if seq else "pos_by_user"], c_pos, hp, out_dtype=xfer)   # dL/du partials, all users
+    g_uf = prims.wsum(st["pos_by_user_p" if seq else "pos_by_user"], c_pos, hp,
+                      out=comm.partial(n_u_pad, hp.size(1), pdt), out_dtype=xfer)              # dL/du partials, all users
     g_uf = prims.wsum(neg_by_user, c_neg, hp, out=g_uf, accumulate=True)
-    pend_u = (reduce_scatter_rows_async(g_uf), None, hu)        # (partials in flight, local term, gate)
+    # partials in flight; the owner adds its local term and applies the ReLU backward (gate = hu)
+    pend_u = comm.reduce_finish_async(g_uf, dtype, prims, relu_of=hu)
     loss_local = (l_pos + l_neg).reshape(())
     del g_uf, c_pos, c_neg, neg_by_post, neg_by_user, hu, hp
 
@@ -233,12 +301,12 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
         g_uf = g_hp = None
         if li > 0:
             g_me, g_hp = prims.proj_bwd_input(dz_p, [(p.lin_l.weight, 1.0, rel_e.inv_deg), (p.lin_r.weight, 1.0, None)])
-            g_uf = prims.gather_sum(rel_e, "bwd", g_me, out_dtype=xfer)      # d user_full partials (engages^T)
+            g_uf = prims.gather_sum(rel_e, "bwd", g_me, out=comm.partial(n_u_pad, g_me.size(1), pdt),
+                                    out_dtype=xfer)                      # d user_full partials (engages^T)
             del g_me
         del dz_p, mean_e
-        rs, g_loc, act = pend_u
-        dz_u = prims.rows_finish(rs.wait(), dtype, add=g_loc, relu_of=act)     # (+ local term), ReLU backward
-        del g_loc, act, pend_u
+        dz_u = pend_u.wait()                                  # reduced (+ local term), ReLU backward applied
+        del pend_u
         (dw_d, dw_s, dw_root), db_u = prims.proj_bwd_weight(dz_u, [(mean_d, wd), (mean_s, ws), (hu_in, 1.0)], True)
         del mean_d, mean_s
         _accum(d.lin_l.weight, dw_d)
@@ -255,10 +323,10 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
         g_md, g_ms, g_hu = prims.proj_bwd_input(
             dz_u, [(d.lin_l.weight, wd, prel_d.inv_deg), (s.lin_l.weight, ws, rel_s.inv_deg), (w_root, 1.0, None)])
         del dz_u
-        ag = all_gather_rows_async(g_md)                              # every post owner needs d mean_direct
+        ag = comm.all_gather_rows_async(g_md)                         # every post owner needs d mean_direct
         g_uf = prims.gather_sum(rel_s, "bwd", g_ms, out=g_uf, accumulate=True)      # || all-gather
-        pend_u = (reduce_scatter_rows_async(g_uf), g_hu, hu_in)
-        del g_uf, g_ms
+        pend_u = comm.reduce_finish_async(g_uf, dtype, prims, add=g_hu, relu_of=hu_in)
+        del g_uf, g_ms, g_hu
         g_md_full = ag.wait()
         dz_p = prims.gather_sum(rel_d, "bwd", g_md_full, out=g_hp, accumulate=True, relu_of=hp_in)  # || reduce-scatter
         del g_md_full, g_md
@@ -288,7 +356,8 @@ def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global
         from .train import stage_negatives
         neg_p_local, neg_ready = stage_negatives(neg_p_local, shard.x_local["user"].device)
     loss = loss_and_grads_sharded(model, shard, neg_p_local, prims, neg_ready=neg_ready, neg_p_global=neg_p_global,
-                                  neg_capacity=neg_capacity).clone()
+                                  neg_capacity=neg_capacity,
+                                  comm=comm_for(model, shard) if prims is CUDA_STEP_PRIMS else LIBRARY_COMM).clone()
     lw = dist.all_reduce(loss, async_op=True)
     allreduce_grads(list(model.parameters()))
     optimizer.step()

@@ -174,6 +174,35 @@ def rows_finish(x, dtype, row_scale=None, add=None, relu_of=None, out=None):
     return out
 
 
+def peer_reduce_rows(parts, row0, n_rows, dtype, row_scale=None, add=None, relu_of=None, ctas_per_sm=0):
+    """``gate(row_scale * sum_g parts[g][row0:row0+n_rows] + add)`` rounded once to ``dtype``
+    (``trg_peer_reduce_rows``): the reduce-scatter of a partial-sum table fused with its row finish.
+    ``parts``: one ``[>= row0 + n_rows, feat]`` table per rank, in rank order -- tensors of this device or of
+    peers (``peer.PeerComm`` passes raw peer-mapped pointers instead); fp32 or ``dtype``."""
+    import ctypes
+    lib = _lib.load()
+    feat = parts[0].size(1)
+    for t in parts:
+        if t.dtype != parts[0].dtype or t.size(1) != feat or t.size(0) < row0 + n_rows or not t.is_contiguous():
+            raise _lib.TrgError("peer_reduce_rows: partial tables must be contiguous, of one dtype and width, and "
+                                "hold rows [row0, row0 + n_rows)")
+    if parts[0].dtype != dtype and parts[0].dtype != torch.float32:
+        raise _lib.TrgError(f"peer_reduce_rows: partial tables must be {dtype} or float32")
+    for t, what in ((add, "add"), (relu_of, "relu_of")):
+        if t is not None and (tuple(t.shape) != (n_rows, feat) or t.dtype != dtype or not t.is_contiguous()):
+            raise _lib.TrgError(f"peer_reduce_rows: {what} must be a contiguous [{n_rows}, {feat}] {dtype} tensor")
+    out = torch.empty(n_rows, feat, dtype=dtype, device=parts[0].device)
+    _check_rows(out, "peer_reduce_rows")
+    rs = row_scale.float().contiguous() if row_scale is not None else None
+    ptrs = (ctypes.c_void_p * len(parts))(*[_lib.ptr(t) for t in parts])
+    nbytes = n_rows * feat * (len(parts) * parts[0].element_size()
+                              + out.element_size() * (1 + (add is not None) + (relu_of is not None)))
+    _lib.call("trg_peer_reduce_rows", nbytes, lib.trg_peer_reduce_rows, ptrs, len(parts), row0,
+              _lib.dtype_code(parts[0].dtype), _lib.ptr(rs), _lib.ptr(add), _lib.ptr(relu_of), n_rows, feat,
+              _lib.dtype_code(dtype), _lib.ptr(out), ctas_per_sm, _lib.stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # K4: link-prediction loss (train_gnn.py:259-281) and its backward
 # ------------------------------------------------------------------------------------------
