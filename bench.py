@@ -285,7 +285,11 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
     neg_host = [t.cpu().pin_memory() for t in neg_dev] if e2e else None
     torch.cuda.synchronize()
 
-    def step(i, host):
+    # N > 1: the step is replayed from a CUDA graph captured on its first call (the eager step is host-bound at
+    # 8 GPUs); TRG_DIST_GRAPH=0 keeps it eager (A/B)
+    graphed = world > 1 and os.environ.get("TRG_DIST_GRAPH", "1") != "0" and os.environ.get("TRG_DIST_TAPE") != "1"
+
+    def step(i, host, eager=False):
         # host: the pinned HOST tensor goes straight into the public API, which copies it in (on a side
         # stream, overlapped with the forward pass: the negatives are first needed by the loss)
         neg = neg_host[i % n_host] if host else neg_dev[i % n_host]
@@ -293,7 +297,8 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
             if os.environ.get("TRG_DIST_TAPE") == "1":      # A/B: autograd Functions + blocking collectives
                 return tdist.train_step_sharded(model, opt, shard, neg_p_global=neg.to(dev, non_blocking=True),
                                                 return_tensor=not host)
-            return dist_fused.train_step_sharded_fused(model, opt, shard, neg_p_global=neg, return_tensor=not host)
+            return dist_fused.train_step_sharded_fused(model, opt, shard, neg_p_global=neg, return_tensor=not host,
+                                                       cuda_graph=graphed and not eager)
         return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
                               g.interaction_type_tensor, U, P, neg_p=neg, return_tensor=not host)
 
@@ -305,7 +310,7 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
     # ---- timed region 1: resident inputs (value) ----
     clocks = ClockSampler(dev.index or 0)
     _lib.PROF.reset()
-    _lib.PROF.enabled = True
+    _lib.PROF.enabled = not graphed          # per-kernel CUDA events: inside the timed region when it is eager
     _barrier(world); torch.cuda.synchronize()
     n0 = _lib.launch_count()
     clocks.start()
@@ -339,7 +344,20 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
         ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
 
     launches = n1 - n0
+    if graphed:
+        # the timed region replayed a graph: its kernels are counted from the capture, and the per-kernel
+        # breakdown comes from an EAGER pass of the same steps (same kernels, launched one by one)
+        launches = steps * shard._graphed.launches_per_replay
+        _lib.PROF.reset()
+        _lib.PROF.enabled = True
+        for i in range(steps):
+            step(i, False, eager=True)
+        torch.cuda.synchronize(); _barrier(world)
+        _lib.PROF.enabled = False
+        prof = _lib.PROF.summary()
     h2d = int(neg_dev[0].numel()) * 8
+    if shard is not None and getattr(shard, "_neg_gather", None) is not None:
+        h2d = shard._neg_gather.chunk * 8          # this rank uploads its 1/N slice; the rest arrives over NVLink
     if world > 1:
         t = torch.tensor([ms, ms_e2e or 0.0], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -352,7 +370,7 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
     del model, opt, shard, g, neg_dev, neg_host
     torch.cuda.empty_cache()
     return dict(ms=ms, ms_e2e=ms_e2e, mp_edges=mp_edges, prof=prof, launches=launches, clocks=clk, host_ms=host_ms,
-                setup_s=setup_s, h2d=h2d, d2h=4 * world, mem_gb=mem_gb, loss=float(loss))
+                setup_s=setup_s, h2d=h2d, d2h=4 * world, mem_gb=mem_gb, loss=float(loss), graphed=graphed)
 
 
 def sub_line(name, w, r, world, steps):
@@ -529,12 +547,16 @@ def main():
             "config": config_of(args.workload, w),
             "parallelism": "single GPU" if world == 1 else
                            f"dst-partitioned x{world}: all-gather of user rows per layer, push partial sums reduce-scattered "
-                           f"(fp32 transport), collectives overlapped with kernels (dist_fused); each rank selects its share "
-                           f"of the step's negatives inside the timed region",
+                           f"(fp32 transport) by copy-engine pulls + a fused reduce/finish kernel over peer memory, collectives overlapped with kernels (dist_fused); each rank selects its share "
+                           f"of the step's negatives inside the timed region"
+                           + ("; the whole step is one CUDA-graph replay (kernels_* from an eager pass of the same steps)"
+                              if r.get("graphed") else ""),
             "e2e": {"value": r["mp_edges"] / r["ms_e2e"] * 1e3, "unit": UNIT, "ms_per_step": r["ms_e2e"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "what": "train_step() via the public API; per step the sampled negatives (int64[E_eng]) are "
-                            "copied from pinned host memory (on every rank) and loss.item() is read back; graph + "
+                            "copied from pinned host memory (N = 1: the whole array; N > 1: every rank holds the array "
+                            "on its host, uploads a 1/N slice and pulls the other slices from its peers over NVLink) "
+                            "and loss.item() is read back; graph + "
                             "features stay resident as in the reference (graph.to(device) once, train_gnn.py:211)"},
             "gpu_launches": r["launches"],
             "clocks": r["clocks"],

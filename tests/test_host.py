@@ -164,3 +164,23 @@ def test_hetero_inputs_follow_train_gnn_assembly():
     assert ei[trg.REL_ENGAGE].tolist() == [[0, 3], [1, 6]]
     assert torch.equal(ei[trg.REL_DIRECT], ei[trg.REL_ENGAGE].flip(0))
     assert torch.equal(ei[trg.REL_SOCIAL], data["edge_index_social"])
+
+
+def test_negative_share_capacity_covers_randint_modulo_bias():
+    """``torch.randint(0, P, (E,))`` (train_gnn.py:272) draws 32 bits and reduces them ``% P``: ids below
+    ``2^32 mod P`` are ``1 / floor(2^32 / P)`` more likely.  At config 4 (P = 50M, E = 800M, 8 ranks) that is
+    +117 000 entries on a rank's 100M share -- beyond 8 sigma of the binomial count -- and overflowed the
+    fixed-capacity selection (found by running config 4; r2).  The capacity must cover the biased expectation."""
+    from truth_recommendation_gnn_b200.dist import ShardedGraph
+    for P, E, world in ((50_000_000, 800_000_000, 8), (5_000_000, 40_000_000, 8), (70_003, 600_000, 2), (7, 100, 2)):
+        sh = ShardedGraph.__new__(ShardedGraph)
+        sh.num_posts, sh.n_pos_global, sh.world = P, E, world
+        sh.cp = (P + world - 1) // world
+        cap = sh.neg_capacity()
+        q = 2**32 // P
+        worst = E * sh.cp * (q + 1) / 2.0**32                 # expected share of the most favoured rank
+        assert cap <= E
+        assert cap >= min(E, worst + 7.9 * worst ** 0.5), (P, E, world, cap, worst)
+    # the observed overflow: 100 132 949 selected at config 4
+    sh.num_posts, sh.n_pos_global, sh.world, sh.cp = 50_000_000, 800_000_000, 8, 6_250_000
+    assert sh.neg_capacity() > 100_132_949

@@ -197,12 +197,15 @@ __global__ void __launch_bounds__(kThreads) gather_reduce(const GatherArgs a) {
 // are prefetched while the current chunk's rows are in flight, and the running sum is flushed at
 // row boundaries.  Removes the per-row rowptr -> col -> row dependency chain that made short rows
 // (in-degree ~8) latency-bound (profiles/README.md, r1_v1).  Same CSR-order adds: still bit-exact.
-template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT, int VB = 16, bool OUTF32 = false>
-__global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) gather_reduce_seg(const GatherArgs a) {
+// UN (0 = default): row loads in flight per lane.  Measured on 256-byte rows (bf16 H = 128, 8-byte lanes): 16 in
+// flight at 3 CTAs / SM is SLOWER than 8 at 4 CTAs / SM (agg_fwd 15.5 vs 12.0 ms at config 3): that shape is not
+// short of loads in flight (profiles/README.md, r2).
+template <typename T, int LPR, int VPL, int MODE, int R, bool VIRT, int VB = 16, bool OUTF32 = false, int UN = 0>
+__global__ void __launch_bounds__(kThreads, UN > 8 ? 3 : (VPL == 1 ? 4 : 2)) gather_reduce_seg(const GatherArgs a) {
   using V = Vec<T, VB>;
   constexpr int kVec = V::kVec;
   constexpr int kOutMul = OUTF32 ? 4 / (int)sizeof(T) : 1;
-  constexpr int kUnroll = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2);
+  constexpr int kUnroll = UN > 0 ? UN : (VPL == 1 ? 8 : (VPL == 2 ? 4 : 2));
   static_assert(R < LPR, "row boundaries are held one per lane");
   const int lane = threadIdx.x & 31;
   const int gl = lane & (LPR - 1);

@@ -29,7 +29,7 @@ def _err(a, b):
 
 
 def check_sharded_against_single(device, dtype=torch.float32, fused=True, sizes=(20_011, 70_003, 600_000, 150_000),
-                                 hidden=128, layers=2, from_generator=False):
+                                 hidden=128, layers=2, from_generator=False, graph=True):
     """Returns ``dict(emb_err, loss_err, grad_err, topk_ids_equal, ok, ...)``, identical on every rank."""
     U, P, EE, ES = sizes
     world = dist.get_world_size()
@@ -66,18 +66,30 @@ def check_sharded_against_single(device, dtype=torch.float32, fused=True, sizes=
         l_mod = tdist.train_step_sharded(mod, o_mod, shard, neg_p_global=neg)
     loss_err = abs(l_mod - l_ref) / abs(l_ref)
     grad_err = max(_err(a.grad.float(), b.grad.float()) for a, b in zip(mod.parameters(), ref.parameters()))
+    graph_err = None
+    if fused and graph:
+        # the same step replayed from its CUDA graph (first call captures, second replays): same loss, same grads
+        o_g = torch.optim.SGD(mod.parameters(), lr=0.0)
+        for _ in range(2):
+            l_g = dist_fused.train_step_sharded_fused(mod, o_g, shard, neg_p_global=neg, cuda_graph=True)
+        graph_err = max(abs(l_g - l_ref) / abs(l_ref),
+                        max(_err(a.grad.float(), b.grad.float()) / 5 for a, b in zip(mod.parameters(), ref.parameters())))
+        shard._graphed = None
     # sharded catalogue top-k == unsharded (ids bit-equal: the same scores row by row)
     q = full["user"][:257].contiguous()
     ev, ei = score_topk(q, full["post"].contiguous(), 100)
     sv, si = tdist.recommend_sharded(q, full["post"][shard.p0:shard.p1].contiguous(), 100, shard.p0)
     ids_equal = bool(torch.equal(si, ei)) and bool(torch.equal(sv, ev))
-    t = torch.tensor([emb_err, loss_err, grad_err, 0.0 if ids_equal else 1.0], device=device, dtype=torch.float64)
+    t = torch.tensor([emb_err, loss_err, grad_err, 0.0 if ids_equal else 1.0, graph_err or 0.0], device=device,
+                     dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)              # worst rank
-    emb_err, loss_err, grad_err, bad_ids = (float(x) for x in t)
+    emb_err, loss_err, grad_err, bad_ids, graph_err_w = (float(x) for x in t)
     tol = TOL[dtype]
     return dict(world=world, dtype=str(dtype).replace("torch.", ""), path="fused" if fused else "tape",
                 graph=f"{U} users / {P} posts / {EE + ES} edges, H={hidden}, L={layers}"
                       + (" (counter-based, sharded without materialising)" if from_generator else ""),
                 emb_err=emb_err, loss_err=loss_err, grad_err=grad_err, topk_ids_equal=bad_ids == 0.0, tol=tol,
                 grad_tol=5 * tol,     # gradients: sums over all nodes of signed terms, as in tests/ (5 x tol)
-                ok=bool(emb_err <= tol and loss_err <= tol and grad_err <= 5 * tol and bad_ids == 0.0), loss=l_mod)
+                graph_replay_err=graph_err_w if graph_err is not None else None,    # max(loss err, grad err / 5)
+                ok=bool(emb_err <= tol and loss_err <= tol and grad_err <= 5 * tol and bad_ids == 0.0
+                        and graph_err_w <= tol), loss=l_mod)

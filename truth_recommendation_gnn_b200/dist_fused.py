@@ -80,6 +80,9 @@ class LibraryComm:
     """The bandwidth collectives as ``torch.distributed`` calls (NCCL kernels on the GPU box -- the A/B of the
     peer-memory path --, gloo in the CPU tests of this host logic)."""
 
+    def begin_step(self):
+        pass
+
     def all_gather_rows_async(self, x_local):
         return all_gather_rows_async(x_local)
 
@@ -97,6 +100,9 @@ class PeerMemoryComm:
 
     def __init__(self, pc):
         self.pc = pc
+
+    def begin_step(self):
+        self.pc.begin_step()
 
     def all_gather_rows_async(self, x_local):
         return self.pc.all_gather_rows_async(x_local)
@@ -120,10 +126,12 @@ def comm_for(model, shard: ShardedGraph):
     x = shard.x_local["user"]
     c = LIBRARY_COMM
     import os
-    if x.is_cuda and dist.get_backend() == "nccl" and os.environ.get("TRG_DIST_COMM", "peer") != "nccl":
+    mode = os.environ.get("TRG_DIST_COMM", "peer")       # peer (= peer-staged) | peer-direct | nccl
+    if x.is_cuda and dist.get_backend() == "nccl" and mode != "nccl":
         from .peer import peer_comm_for
         feat = max([x.size(1), shard.x_local["post"].size(1)] + [int(p.size(0)) for p in model.parameters() if p.dim() == 2])
-        c = PeerMemoryComm(peer_comm_for(shard, feat, x.dtype, transport_dtype(x.dtype)))
+        c = PeerMemoryComm(peer_comm_for(shard, feat, x.dtype, transport_dtype(x.dtype),
+                                         reduce_mode="direct" if mode == "peer-direct" else "staged"))
     shard._comm = c
     return c
 
@@ -236,6 +244,7 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     xfer = transport_dtype(dtype)
     pdt = xfer or dtype                                 # element type of the partial-sum tables
     comm = comm or LIBRARY_COMM
+    comm.begin_step()
 
     # ---- forward ----
     saved = []
@@ -333,15 +342,108 @@ def loss_and_grads_sharded(model, shard: ShardedGraph, neg_p_local, prims=CUDA_S
     return loss_local
 
 
+class GraphedShardedStep:
+    """The sharded step -- forward, loss, backward, every collective, the gradient all-reduce -- captured ONCE
+    into a CUDA graph and replayed per step (``train_step_sharded_fused(..., cuda_graph=True)``).
+
+    At 8 GPUs one step is ~9 ms of GPU work behind ~85 kernel launches, ~60 copy-engine transfers and ~120
+    stream/event operations: enqueueing them from Python takes as long as executing them (9 - 11 ms measured),
+    so the eager step is host-bound.  The replay is one launch.  What stays outside the graph: the upload of
+    this step's negatives into the graph's static input (``HostSliceGather`` for host arrays), the optimiser's
+    own ``step()`` (the caller's ``torch.optim`` object, untouched) and the loss read-back.
+
+    Capture happens on the first call, after two eager steps' worth of warm-up with that call's negatives
+    (structures and lazy weights materialise there; the optimiser is NOT stepped during warm-up).  The
+    parameters' ``.grad`` tensors live in the graph's memory pool and are rewritten by every replay, so
+    ``optimizer.zero_grad()`` is not needed (and must not set them to None) between graphed steps."""
+
+    def __init__(self, model, optimizer, shard: ShardedGraph, neg_capacity=None):
+        if not eligible(model, shard) or not shard.x_local["user"].is_cuda:
+            raise ValueError("GraphedShardedStep needs a CUDA shard and a model the tape-free sharded step accepts")
+        self.model, self.optimizer, self.shard, self.neg_capacity = model, optimizer, shard, neg_capacity
+        self.comm = comm_for(model, shard)
+        dev = shard.x_local["user"].device
+        self.neg = torch.empty(shard.n_pos_global, dtype=torch.int64, device=dev)
+        self.graph = None
+        self.loss = None
+        self.launches_per_replay = 0
+
+    def _body(self):
+        loss = loss_and_grads_sharded(self.model, self.shard, None, CUDA_STEP_PRIMS, neg_p_global=self.neg,
+                                      neg_capacity=self.neg_capacity, comm=self.comm).clone()
+        lw = dist.all_reduce(loss, async_op=True)
+        allreduce_grads(list(self.model.parameters()))
+        lw.wait()
+        return loss
+
+    def _capture(self):
+        from . import _lib
+        if _lib.PROF.enabled:
+            raise _lib.TrgError("GraphedShardedStep: per-call event timing (PROF) cannot run inside a graph capture")
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(self.neg.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):                       # warm-up: structures, lazy weights, allocator
+                self.optimizer.zero_grad(set_to_none=True)
+                self._body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.optimizer.zero_grad(set_to_none=True)
+        if isinstance(self.comm, PeerMemoryComm):
+            self.comm.pc._last_barrier = None        # an event recorded outside the capture cannot be waited inside
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self.loss = self._body()
+        self.launches_per_replay = _lib.launch_count() - n0      # kernels of this library inside one replay
+        self.params = [p for p in self.model.parameters() if p.grad is not None]
+        self.grads = [p.grad for p in self.params]               # static: rewritten by every replay
+        self.graph = g
+
+    def __call__(self, neg_p_global, return_tensor=False):
+        shard = self.shard
+        self.model.train()
+        if neg_p_global is None:
+            neg_p_global = shard.draw_negatives()
+        if neg_p_global.is_cuda:
+            self.neg.copy_(neg_p_global)
+        elif isinstance(self.comm, PeerMemoryComm):
+            hg = getattr(shard, "_neg_gather", None)
+            if hg is None or hg.n != neg_p_global.numel():
+                from .peer import HostSliceGather
+                hg = shard._neg_gather = HostSliceGather(neg_p_global.numel(), neg_p_global.dtype, self.neg.device)
+            _, ev = hg.gather_async(neg_p_global, out=self.neg)
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            self.neg.copy_(neg_p_global, non_blocking=True)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):                # (an eager step in between may have re-pointed them)
+            p.grad = g
+        self.optimizer.step()
+        return self.loss if return_tensor else self.loss.item()
+
+
 def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global=None, neg_p_local=None,
-                             prims=CUDA_STEP_PRIMS, return_tensor=False, neg_capacity=None):
+                             prims=CUDA_STEP_PRIMS, return_tensor=False, neg_capacity=None, cuda_graph=False):
     """``dist.train_step_sharded`` without the tape and with the collectives overlapped.
 
     ``neg_p_global``: the step's ``torch.randint(0, P, (E,))`` (train_gnn.py:272) -- the SAME array on every
     rank, device or (pinned) host; ``None`` draws it from the shard's rank-synchronised generator.  Each rank
     keeps the pairs whose negative post it owns; that selection runs on the device inside the step with no
     host synchronisation (``ShardedGraph.select_negatives``; ``neg_capacity`` overrides its room).
-    ``neg_p_local``: a share already selected by the caller (``shard.local_negatives``)."""
+    ``neg_p_local``: a share already selected by the caller (``shard.local_negatives``).
+    ``cuda_graph``: replay the step from a CUDA graph captured on the first call (``GraphedShardedStep``)."""
+    if cuda_graph:
+        if neg_p_local is not None or prims is not CUDA_STEP_PRIMS:
+            raise ValueError("cuda_graph=True takes the step's global negatives and the CUDA primitives")
+        gs = getattr(shard, "_graphed", None)
+        if gs is None or gs.model is not model or gs.optimizer is not optimizer:
+            gs = shard._graphed = GraphedShardedStep(model, optimizer, shard, neg_capacity)
+        return gs(neg_p_global, return_tensor=return_tensor)
     model.train()
     optimizer.zero_grad()
     is_cuda = shard.x_local["user"].is_cuda
@@ -350,8 +452,17 @@ def train_step_sharded_fused(model, optimizer, shard: ShardedGraph, neg_p_global
         if neg_p_global is None:
             neg_p_global = shard.draw_negatives()          # rank-synchronised generator: same array everywhere
         if not neg_p_global.is_cuda and is_cuda:
-            from .train import stage_negatives
-            neg_p_global, neg_ready = stage_negatives(neg_p_global, shard.x_local["user"].device)
+            if prims is CUDA_STEP_PRIMS and isinstance(comm_for(model, shard), PeerMemoryComm):
+                # every rank holds the same host array: upload 1/G of it, pull the rest over NVLink
+                hg = getattr(shard, "_neg_gather", None)
+                if hg is None or hg.n != neg_p_global.numel():
+                    from .peer import HostSliceGather
+                    hg = shard._neg_gather = HostSliceGather(neg_p_global.numel(), neg_p_global.dtype,
+                                                             shard.x_local["user"].device)
+                neg_p_global, neg_ready = hg.gather_async(neg_p_global)
+            else:
+                from .train import stage_negatives
+                neg_p_global, neg_ready = stage_negatives(neg_p_global, shard.x_local["user"].device)
     elif torch.is_tensor(neg_p_local) and not neg_p_local.is_cuda and is_cuda:
         from .train import stage_negatives
         neg_p_local, neg_ready = stage_negatives(neg_p_local, shard.x_local["user"].device)
