@@ -367,7 +367,13 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
         launches, h2d = int(c[0]), int(c[1])
     mp_edges = L * (2 * Ee + Es)
     mem_gb = torch.cuda.max_memory_allocated(dev) / 2**30
+    loss = float(loss)
+    if shard is not None and getattr(shard, "_graphed", None) is not None:
+        shard._graphed.close()          # the graph holds captured NCCL work: drop it before the group goes away
+        shard._graphed = None
     del model, opt, shard, g, neg_dev, neg_host
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return dict(ms=ms, ms_e2e=ms_e2e, mp_edges=mp_edges, prof=prof, launches=launches, clocks=clk, host_ms=host_ms,
                 setup_s=setup_s, h2d=h2d, d2h=4 * world, mem_gb=mem_gb, loss=float(loss), graphed=graphed)
@@ -596,8 +602,16 @@ def main():
                     line["topk"]["cpu_baseline"] = cpu_topk_baseline(6.0)
         print(json.dumps(line))
     if world > 1:
+        # teardown must not be able to hang the job after the line is out
+        import threading
+        sys.stdout.flush()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        torch.cuda.synchronize()
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":

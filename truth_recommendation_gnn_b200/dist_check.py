@@ -74,6 +74,7 @@ def check_sharded_against_single(device, dtype=torch.float32, fused=True, sizes=
             l_g = dist_fused.train_step_sharded_fused(mod, o_g, shard, neg_p_global=neg, cuda_graph=True)
         graph_err = max(abs(l_g - l_ref) / abs(l_ref),
                         max(_err(a.grad.float(), b.grad.float()) / 5 for a, b in zip(mod.parameters(), ref.parameters())))
+        shard._graphed.close()
         shard._graphed = None
     # sharded catalogue top-k == unsharded (ids bit-equal: the same scores row by row)
     q = full["user"][:257].contiguous()

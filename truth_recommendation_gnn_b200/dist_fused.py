@@ -364,13 +364,17 @@ class GraphedShardedStep:
         self.comm = comm_for(model, shard)
         dev = shard.x_local["user"].device
         self.neg = torch.empty(shard.n_pos_global, dtype=torch.int64, device=dev)
+        # "this step's negatives are in self.neg": an EXTERNAL event -- inside the graph it is an event-wait
+        # node placed right before the negatives are first read (the loss), so the upload of a step's host
+        # negatives overlaps the replayed forward pass exactly as in the eager step
+        self.neg_ready = torch.cuda.Event(external=True)
         self.graph = None
         self.loss = None
         self.launches_per_replay = 0
 
     def _body(self):
-        loss = loss_and_grads_sharded(self.model, self.shard, None, CUDA_STEP_PRIMS, neg_p_global=self.neg,
-                                      neg_capacity=self.neg_capacity, comm=self.comm).clone()
+        loss = loss_and_grads_sharded(self.model, self.shard, None, CUDA_STEP_PRIMS, neg_ready=self.neg_ready,
+                                      neg_p_global=self.neg, neg_capacity=self.neg_capacity, comm=self.comm).clone()
         lw = dist.all_reduce(loss, async_op=True)
         allreduce_grads(list(self.model.parameters()))
         lw.wait()
@@ -402,22 +406,27 @@ class GraphedShardedStep:
         self.grads = [p.grad for p in self.params]               # static: rewritten by every replay
         self.graph = g
 
+    def close(self):
+        """Drop the captured graph (and with it the NCCL work it holds): a process group must not be destroyed
+        while a graph that captured its collectives is alive."""
+        self.graph = None
+        self.loss = None
+        self.params, self.grads = [], []
+
     def __call__(self, neg_p_global, return_tensor=False):
         shard = self.shard
         self.model.train()
         if neg_p_global is None:
             neg_p_global = shard.draw_negatives()
-        if neg_p_global.is_cuda:
-            self.neg.copy_(neg_p_global)
-        elif isinstance(self.comm, PeerMemoryComm):
+        if not neg_p_global.is_cuda and isinstance(self.comm, PeerMemoryComm):
             hg = getattr(shard, "_neg_gather", None)
             if hg is None or hg.n != neg_p_global.numel():
                 from .peer import HostSliceGather
                 hg = shard._neg_gather = HostSliceGather(neg_p_global.numel(), neg_p_global.dtype, self.neg.device)
-            _, ev = hg.gather_async(neg_p_global, out=self.neg)
-            torch.cuda.current_stream().wait_event(ev)
+            hg.gather_async(neg_p_global, out=self.neg, event=self.neg_ready)     # side stream: overlaps the forward
         else:
             self.neg.copy_(neg_p_global, non_blocking=True)
+            self.neg_ready.record()
         if self.graph is None:
             self._capture()
         self.graph.replay()

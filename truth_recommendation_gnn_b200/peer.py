@@ -236,9 +236,10 @@ class HostSliceGather:
         self.stream = torch.cuda.Stream(device)
         self._calls = 0
 
-    def gather_async(self, host, out=None):
+    def gather_async(self, host, out=None, event=None):
         """-> (device tensor [n], event).  ``host``: the full array, identical on every rank; ``out``: a device
-        tensor to fill (the static input of a captured step) instead of a fresh one."""
+        tensor to fill (the static input of a captured step) instead of a fresh one; ``event``: the event to
+        record when the array is complete (a captured step waits on an ``external`` event) instead of a new one."""
         if host.is_cuda or host.dtype != self.dtype or host.numel() != self.n:
             raise _lib.TrgError(f"HostSliceGather: expected a host {self.dtype} tensor of {self.n} elements")
         idx = self._calls % 2
@@ -258,7 +259,7 @@ class HostSliceGather:
                 a, b = min(p * c, self.n), min((p + 1) * c, self.n)
                 if b > a:
                     out[a:b].copy_(self._peers[idx][p][:b - a])
-            ev = torch.cuda.Event()
+            ev = event if event is not None else torch.cuda.Event()
             ev.record(self.stream)
         out.record_stream(self.stream)
         return out, ev
