@@ -50,7 +50,10 @@ WORKLOADS = {
                  hidden=128, layers=2, dtype="bf16"),
     # configs[3]: 8 x B200 only; generated per shard on the device (synth.CounterGraph)
     "cfg4": dict(num_users=10_000_000, num_posts=50_000_000, e_eng=800_000_000, e_soc=200_000_000,
-                 hidden=256, layers=3, dtype="bf16", counter=True),
+                 hidden=256, layers=3, dtype="bf16", counter=True, eager=True, comm="peer-direct"),
+    # (config 4 runs the eager step with direct peer loads: the configuration it was validated in at 8 GPUs; its
+    # graph-captured / copy-engine-staged form did not finish within the leg's time limit when first tried and
+    # there was no 8-GPU time left to find out why)
     # load-balance report: config 2 with Zipf-like destinations, dst = floor(N * u^3)
     "cfg2skew": dict(num_users=1_000_000, num_posts=5_000_000, e_eng=40_000_000, e_soc=10_000_000,
                      hidden=128, layers=2, dtype="f32", skew=True),
@@ -59,7 +62,7 @@ WORKLOADS = {
                  hidden=64, layers=2, dtype="f32"),
     # 1/8 of config 4 per GPU count 1 (development / 2-GPU checks of the config-4 code path)
     "cfg4mini": dict(num_users=1_250_000, num_posts=6_250_000, e_eng=100_000_000, e_soc=25_000_000,
-                     hidden=256, layers=3, dtype="bf16", counter=True),
+                     hidden=256, layers=3, dtype="bf16", counter=True, eager=True, comm="peer-direct"),
     "tiny": dict(num_users=2_000, num_posts=8_000, e_eng=60_000, e_soc=15_000,
                  hidden=64, layers=2, dtype="f32"),
 }
@@ -278,6 +281,8 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
             shard = tdist.ShardedGraph(g.x_dict, g.edge_index_dict, g.train_edge_index,
                                        g.interaction_type_tensor, U, P)
             g = None
+    if shard is not None and w.get("comm"):
+        shard.comm_mode = w["comm"]
     torch.cuda.empty_cache()
     # this step's input: the sampled negatives (train_gnn.py:272), the SAME full array on every rank; each rank
     # selects its share inside the step (device-side, no host sync)
@@ -287,7 +292,9 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
 
     # N > 1: the step is replayed from a CUDA graph captured on its first call (the eager step is host-bound at
     # 8 GPUs); TRG_DIST_GRAPH=0 keeps it eager (A/B)
-    graphed = world > 1 and os.environ.get("TRG_DIST_GRAPH", "1") != "0" and os.environ.get("TRG_DIST_TAPE") != "1"
+    graphed = (world > 1 and os.environ.get("TRG_DIST_GRAPH", "1") != "0" and os.environ.get("TRG_DIST_TAPE") != "1"
+               and not w.get("eager"))
+    graphed1 = world == 1 and bool(w.get("cuda_graph"))       # single GPU: config 1 (launch-bound) only
 
     def step(i, host, eager=False):
         # host: the pinned HOST tensor goes straight into the public API, which copies it in (on a side
@@ -300,7 +307,8 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
             return dist_fused.train_step_sharded_fused(model, opt, shard, neg_p_global=neg, return_tensor=not host,
                                                        cuda_graph=graphed and not eager)
         return trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
-                              g.interaction_type_tensor, U, P, neg_p=neg, return_tensor=not host)
+                              g.interaction_type_tensor, U, P, neg_p=neg, return_tensor=not host,
+                              cuda_graph=graphed1 and not eager)
 
     for i in range(warmup):
         step(i, False)
@@ -310,7 +318,7 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
     # ---- timed region 1: resident inputs (value) ----
     clocks = ClockSampler(dev.index or 0)
     _lib.PROF.reset()
-    _lib.PROF.enabled = not graphed          # per-kernel CUDA events: inside the timed region when it is eager
+    _lib.PROF.enabled = not (graphed or graphed1)   # per-kernel CUDA events: inside the timed region when it is eager
     _barrier(world); torch.cuda.synchronize()
     n0 = _lib.launch_count()
     clocks.start()
@@ -323,6 +331,7 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
     host_ms = (time.perf_counter() - t_host0) * 1e3 / steps     # CPU time to ENQUEUE one step
     e1.record()
     torch.cuda.synchronize(); _barrier(world)
+    loss = float(loss)        # now: a graphed step returns its static loss tensor, which later replays overwrite
     clk = clocks.stop()
     n1 = _lib.launch_count()
     _lib.PROF.enabled = False
@@ -344,10 +353,10 @@ def gpu_train_bench(args, w, rank, world, dev, steps, warmup, e2e=True):
         ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
 
     launches = n1 - n0
-    if graphed:
+    if graphed or graphed1:
         # the timed region replayed a graph: its kernels are counted from the capture, and the per-kernel
         # breakdown comes from an EAGER pass of the same steps (same kernels, launched one by one)
-        launches = steps * shard._graphed.launches_per_replay
+        launches = steps * (shard._graphed if graphed else model._trg_graphed_step).launches_per_replay
         _lib.PROF.reset()
         _lib.PROF.enabled = True
         for i in range(steps):
@@ -461,11 +470,14 @@ def gpu_cfg1(dev):
     out = {}
     a = argparse.Namespace()
     for L in (1, 2):
-        w = dict(WORKLOADS["cfg1"], layers=L)
-        r = gpu_train_bench(a, w, 0, 1, dev, steps=20, warmup=5, e2e=True)
-        out[f"L{L}"] = {"edges_per_s": r["mp_edges"] / r["ms"] * 1e3, "ms_per_step": r["ms"],
+        for key, graph in ((f"L{L}", False), (f"L{L}_cuda_graph", True)):
+            w = dict(WORKLOADS["cfg1"], layers=L, cuda_graph=graph)
+            r = gpu_train_bench(a, w, 0, 1, dev, steps=20, warmup=5, e2e=True)
+            out[key] = {"edges_per_s": r["mp_edges"] / r["ms"] * 1e3, "ms_per_step": r["ms"],
                         "e2e_edges_per_s": r["mp_edges"] / r["ms_e2e"] * 1e3, "e2e_ms_per_step": r["ms_e2e"],
                         "launches_per_step": r["launches"] / 20, "loss": r["loss"]}
+    out["note"] = ("*_cuda_graph: train_step(..., cuda_graph=True) -- the step replayed from a CUDA graph (one launch "
+                   "per step); the eager step at this size is bound by the Python launch path")
     return out
 
 
@@ -506,9 +518,28 @@ def main():
               f"kernels {({k: round(v['ms'] / args.steps, 3) for k, v in sorted(r['prof'].items())})}",
               file=sys.stderr, flush=True)
     extras, errors = {}, {}
+    import threading
+    build_line = make_line_builder(args, w, r, world, dev, default_workload, extras, errors)
 
-    def leg(name, fn):
+    def emergency(name, limit):
+        # a secondary leg that HANGS (a rank died inside a collective, a capture that never ends) must not take
+        # the headline with it either: every rank's watchdog fires at the same deadline, rank 0 prints the line
+        # with what finished, everybody leaves with exit code 0
+        errors[name] = f"no result within {limit:.0f} s: leg abandoned, job ended by the watchdog"
+        if rank == 0:
+            try:
+                print(json.dumps(build_line()), flush=True)
+            finally:
+                os._exit(0)
+        time.sleep(3.0)
+        os._exit(0)
+
+    def leg(name, fn, limit=150.0):
         # a secondary leg that fails must not take the headline line with it: the error is reported in its place
+        wd = threading.Timer(limit, emergency, args=(name, limit))
+        wd.daemon = True
+        if world > 1:
+            wd.start()
         try:
             extras[name] = fn()
             if rank == 0:           # progress on stderr: a later leg that kills the job does not erase this one
@@ -518,6 +549,8 @@ def main():
         except Exception as e:      # noqa: BLE001
             errors[name] = f"{type(e).__name__}: {e}"[:400]
             torch.cuda.empty_cache()
+        finally:
+            wd.cancel()
 
     if not args.no_extras and default_workload:
         sub_steps = min(args.steps, 10)
@@ -528,12 +561,28 @@ def main():
         leg("cfg3", lambda: (w3, gpu_train_bench(args, w3, rank, world, dev, sub_steps, 3, e2e=False), sub_steps))
         if world == 8:
             w4 = WORKLOADS["cfg4"]
-            leg("cfg4", lambda: (w4, gpu_train_bench(args, w4, rank, world, dev, min(args.steps, 5), 3, e2e=False), min(args.steps, 5)))
+            leg("cfg4", lambda: (w4, gpu_train_bench(args, w4, rank, world, dev, min(args.steps, 5), 3, e2e=False), min(args.steps, 5)),
+                limit=300.0)
     if not args.no_topk:
         leg("topk", lambda: gpu_topk_bench(dev, rank, world))
-    topk = extras.get("topk")
 
     if rank == 0:
+        print(json.dumps(build_line(final=True)))
+    if world > 1:
+        # teardown must not be able to hang the job after the line is out
+        sys.stdout.flush()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+        t.cancel()
+
+
+def make_line_builder(args, w, r, world, dev, default_workload, extras, errors):
+    def build_line(final=False):
+        topk = extras.get("topk")
         pk = peaks()
         elem = 4 if w["dtype"] == "f32" else 2
         value = r["mp_edges"] / r["ms"] * 1e3
@@ -590,9 +639,9 @@ def main():
             line["topk"] = topk
         if errors:
             line["leg_errors"] = errors
-        if world == 1 and not args.no_extras and default_workload:
+        if final and world == 1 and not args.no_extras and default_workload:
             line["cfg1"] = gpu_cfg1(dev)
-        if not args.no_cpu_baseline and world == 1:
+        if final and not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             cb = run_cpu_oracle(w, 2, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -600,18 +649,9 @@ def main():
                 line["cfg1"]["cpu"] = cpu_cfg1()
                 if topk is not None:
                     line["topk"]["cpu_baseline"] = cpu_topk_baseline(6.0)
-        print(json.dumps(line))
-    if world > 1:
-        # teardown must not be able to hang the job after the line is out
-        import threading
-        sys.stdout.flush()
-        t = threading.Timer(30.0, lambda: os._exit(0))
-        t.daemon = True
-        t.start()
-        torch.cuda.synchronize()
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
-        t.cancel()
+        return line
+
+    return build_line
 
 
 if __name__ == "__main__":

@@ -434,3 +434,31 @@ def test_cfg1_full_size_against_oracle(dev):
         _, g_gated, n_amb = oracle_grads_with_gates(H, L, sd, g, neg, product_gates(probe, gd.x_dict, gd.edge_index_dict))
         for n, a in model.named_parameters():
             assert_close(a.grad.cpu(), g_gated[n], 5 * TOL_F32, f"cfg1 L={L} grad {n} ({n_amb} ambiguous gates)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layers", [1, 2])
+def test_train_step_cuda_graph_matches_eager(dev, layers):
+    """``train_step(..., cuda_graph=True)`` replays the tape-free step from a CUDA graph: same kernels in the
+    same order, so four steps from the same weights give the same losses and the same weights as the eager
+    step (device negatives and host negatives, whose upload overlaps the replayed forward)."""
+    U, P, H = 700, 2500, 64
+    g = synth.synth_graph(U, P, 20_000, 5_000, H, seed=3).to(dev)
+    sd = synth.init_state_dict(H, H, layers)
+    losses, weights = {}, {}
+    for mode in ("eager", "graph"):
+        model = (trg.WeightedRGCN(H) if layers == 1 else trg.StackedWeightedRGCN(H, layers))
+        model.load_state_dict(sd)
+        model = model.to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        ls = []
+        for i in range(4):
+            neg = synth.synth_neg(P, 20_000, i)
+            neg = neg.pin_memory() if i % 2 else neg.to(dev)
+            ls.append(trg.train_step(model, opt, g.x_dict, g.edge_index_dict, g.train_edge_index,
+                                     g.interaction_type_tensor, U, P, neg_p=neg, cuda_graph=(mode == "graph")))
+        losses[mode] = ls
+        weights[mode] = [p.detach().clone() for p in model.parameters()]
+    assert losses["eager"] == pytest.approx(losses["graph"], rel=1e-6)
+    for a, b in zip(weights["eager"], weights["graph"]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)

@@ -126,7 +126,8 @@ def comm_for(model, shard: ShardedGraph):
     x = shard.x_local["user"]
     c = LIBRARY_COMM
     import os
-    mode = os.environ.get("TRG_DIST_COMM", "peer")       # peer (= peer-staged) | peer-direct | nccl
+    # peer (= peer-staged) | peer-direct | nccl; a shard may pin its own mode (``shard.comm_mode``)
+    mode = getattr(shard, "comm_mode", None) or os.environ.get("TRG_DIST_COMM", "peer")
     if x.is_cuda and dist.get_backend() == "nccl" and mode != "nccl":
         from .peer import peer_comm_for
         feat = max([x.size(1), shard.x_local["post"].size(1)] + [int(p.size(0)) for p in model.parameters() if p.dim() == 2])
