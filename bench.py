@@ -460,8 +460,8 @@ def gpu_topk_bench(dev, rank, world, iters=3):
                 config={"workload": f"cfg5: {batch} queries x {n_post} posts, top-{k}, H={hidden}, bf16 in / fp32 accumulate"
                                     + (f", catalogue sharded over {world} GPUs by post-id range" if world > 1 else "")},
                 batch=batch, n_post=n_post, hidden=hidden, k=k, dtype="bf16 in / fp32 accumulate",
-                kernel="score_topk_tc2_kernel (tcgen05 kind::f16; scan warps read TMEM rows, helper warps keep the "
-                       "top-K lists in TMEM)")
+                kernel="score_topk_tc3_kernel (tcgen05 kind::f16; scan warps read TMEM rows, helper warps keep the "
+                       "per-item top-K lists in TMEM and merge them into the rows' global lists under a row lock)")
 
 
 def gpu_cfg1(dev):

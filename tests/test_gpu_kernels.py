@@ -496,7 +496,7 @@ def test_rows_finish(dev, dtype, in_f32):
 
 
 @pytest.mark.parametrize("dtype,in_f32", [(torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)])
-@pytest.mark.parametrize("n_peers", [1, 2, 3, 8])
+@pytest.mark.parametrize("n_peers", [1, 2, 3, 4, 8])
 def test_peer_reduce_rows(dev, dtype, in_f32, n_peers):
     """trg_peer_reduce_rows = reduce-scatter + trg_rows_finish in one kernel: the owned row range of G partial
     tables summed in rank order (bit-equal to the sequential fp32 sum), then 1/deg, local term, ReLU gate, one

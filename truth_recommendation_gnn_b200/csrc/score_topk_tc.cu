@@ -45,8 +45,11 @@ struct ScoreTcParams {
   int k, n_splits, kblocks;   // kblocks = H / 64
   int dbg;                    // ablation switches, TRG_DEBUG builds only (TRG_TOPK_DBG): 1 = no selection, 2 = no tcgen05.ld either, 4 = no MMA
   int* thr_shared;            // [B] ordered-int keys of the best published K-th score per query row
-  float* part_vals;           // [B][n_splits][k]
+  float* part_vals;           // [B][n_splits][k]   (v1 / v2 kernels: per-split lists, merged by trg_topk_merge)
   long long* part_ids;        // [B][n_splits][k]
+  int* locks;                 // [B] v3: one lock per query row's global list
+  float* out_vals;            // [B][k] v3: the rows' global top-K lists (= the result), merged into by every item
+  long long* out_ids;         // [B][k]
 };
 
 // Ablation / cycle-accounting switches alter results; they exist only in -DTRG_DEBUG builds.
@@ -647,6 +650,96 @@ __device__ __forceinline__ bool next_segment(const ScoreTcParams& p, long long n
   return true;
 }
 
+// Merge a finished item's list of one query row (m_l entries, best first, in shared memory; ids relative to
+// `idbase`) into that row's GLOBAL list -- the kernel's result, [K] scores + [K] int64 ids in global memory --
+// under the row's lock.  Both lists are sorted and ids are unique (an item only holds posts of its own chunk),
+// so every entry's final slot is its own index plus the number of entries of the other list that rank before
+// it (binary searches): a rank merge whose writes never collide.  The new K-th best is published
+// (thr_shared), so the items that start later filter with the exact K-th best of everything finished so far.
+// Why: with per-item lists that restart empty and only share the K-th best of ONE chunk's list, every item
+// inserted >= K candidates per row again (37 chunks x ~150 insertions per row at config 5) and the candidate
+// work was a fixed ~21 ms whatever the catalogue size (65.6 ms at 50M posts, 29.9 ms at 10M: r2 same-box A/B);
+// with the global K-th best the later items insert K x chunk / seen.  gs / gid: scratch for 128 scores / ids.
+__device__ __forceinline__ void merge_into_global(const ScoreTcParams& p, long long gq, uint32_t lv_a, uint32_t li_a,
+                                                  long long idbase, float* gs, long long* gid, int m_l, int K,
+                                                  int lane) {
+  if (lane == 0) {
+    while (atomicCAS(p.locks + gq, 0, 1) != 0) __nanosleep(100);
+    __threadfence();
+  }
+  __syncwarp();
+  float* gv = p.out_vals + gq * K;
+  long long* gi = p.out_ids + gq * K;
+  float s_g[4];
+  long long id_g[4];
+  int mg = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int i = lane + 32 * t;
+    s_g[t] = -INFINITY;
+    id_g[t] = kPadIdTc;
+    if (i < K) {
+      s_g[t] = __ldcg(gv + i);
+      id_g[t] = __ldcg(gi + i);
+    }
+    mg += __popc(__ballot_sync(0xffffffffu, id_g[t] != kPadIdTc));
+    gs[i] = s_g[t];
+    gid[i] = id_g[t];
+  }
+  __syncwarp();
+  // global entries: number of local entries ranking before each
+  int pos_g[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int lo = 0, hi = m_l;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float s = __uint_as_float(lds32(lv_a + 4u * mid));
+      const long long id = idbase + (long long)lds32(li_a + 4u * mid);
+      if (s > s_g[t] || (s == s_g[t] && id < id_g[t])) lo = mid + 1; else hi = mid;
+    }
+    pos_g[t] = lane + 32 * t + lo;
+  }
+  // local entries: number of global entries ranking before each
+  float s_l[4];
+  long long id_l[4];
+  int pos_l[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int i = lane + 32 * t;
+    s_l[t] = -INFINITY;
+    id_l[t] = kPadIdTc;
+    pos_l[t] = K;
+    if (i < m_l) {
+      s_l[t] = __uint_as_float(lds32(lv_a + 4u * i));
+      id_l[t] = idbase + (long long)lds32(li_a + 4u * i);
+      int lo = 0, hi = mg;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (gs[mid] > s_l[t] || (gs[mid] == s_l[t] && gid[mid] < id_l[t])) lo = mid + 1; else hi = mid;
+      }
+      pos_l[t] = i + lo;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (lane + 32 * t < mg && pos_g[t] < K) {
+      gv[pos_g[t]] = s_g[t];
+      gi[pos_g[t]] = id_g[t];
+      if (pos_g[t] == K - 1) atomicMax(p.thr_shared + gq, float_key(s_g[t]));
+    }
+    if (pos_l[t] < K) {
+      gv[pos_l[t]] = s_l[t];
+      gi[pos_l[t]] = id_l[t];
+      if (pos_l[t] == K - 1) atomicMax(p.thr_shared + gq, float_key(s_l[t]));
+    }
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(p.locks + gq, 0);
+}
+
 template <int NS>
 __global__ void __launch_bounds__(512, 1)
     score_topk_tc3_kernel(const __grid_constant__ ScoreTcParams p, int n_stages) {
@@ -666,8 +759,10 @@ __global__ void __launch_bounds__(512, 1)
   uint32_t* si = reinterpret_cast<uint32_t*>(sv + 4 * 128);
   float* cq_s = reinterpret_cast<float*>(si + 4 * 128);                                  // [128][kQStride]
   uint32_t* cq_i = reinterpret_cast<uint32_t*>(cq_s + kQRows * kQStride);
-  uint2* row_thr = reinterpret_cast<uint2*>(
-      (reinterpret_cast<uintptr_t>(cq_i + kQRows * kQStride) + 7) & ~static_cast<uintptr_t>(7));   // (K-th score, K-th id)
+  long long* g_id = reinterpret_cast<long long*>(
+      (reinterpret_cast<uintptr_t>(cq_i + kQRows * kQStride) + 7) & ~static_cast<uintptr_t>(7));   // global-list scratch [4][128] ids
+  float* g_s = reinterpret_cast<float*>(g_id + 4 * 128);                                 //                     [4][128] scores
+  uint2* row_thr = reinterpret_cast<uint2*>(g_s + 4 * 128);                              // (K-th score, K-th id)
   float* row_tg = reinterpret_cast<float*>(row_thr + kQRows);                            // threshold of the other CTAs
   volatile int* ctl = reinterpret_cast<volatile int*>(row_tg + kQRows);                  // [8 rings][4]: head, tail, done
   uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(ctl) + 32);
@@ -1036,27 +1131,29 @@ __global__ void __launch_bounds__(512, 1)
         }
       }
       {
+        // the item is done: merge every row's list into the row's global list (the result)
         const int r = wq * 32 + lane;
-        const bool row_ok = q0 + r < p.n_query;
-        float* ov = p.part_vals + ((q0 + r) * p.n_splits + sg.slot) * K;
-        long long* oi = p.part_ids + ((q0 + r) * p.n_splits + sg.slot) * K;
         const long long idbase = p.id_offset + sg.tile0 * N;
+        for (int L = 0; L < 32; ++L) {
+          const int m_l = __shfl_sync(0xffffffffu, m, L);
+          const long long gq = q0 + wq * 32 + L;
+          if (m_l == 0 || gq >= p.n_query) continue;
 #pragma unroll 1
-        for (int c = 0; c * 16 < K; ++c) {
-          uint32_t rs[16], ri[16];
-          tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
-          tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
-          tmem_ld_wait();
-          if (row_ok) {
+          for (int c = 0; c * 16 < m_l; ++c) {
+            uint32_t rs[16], ri[16];
+            tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
+            tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
+            tmem_ld_wait();
+            if (lane == L) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int i = c * 16 + j;
-              if (i < K) {
-                ov[i] = i < m ? __uint_as_float(rs[j]) : -INFINITY;
-                oi[i] = i < m ? idbase + (long long)ri[j] : kPadIdTc;
+              for (int j = 0; j < 16; j += 4) {
+                sts128(sv_a + 4u * (uint32_t)(c * 16 + j), make_uint4(rs[j], rs[j + 1], rs[j + 2], rs[j + 3]));
+                sts128(si_a + 4u * (uint32_t)(c * 16 + j), make_uint4(ri[j], ri[j + 1], ri[j + 2], ri[j + 3]));
               }
             }
           }
+          __syncwarp();
+          merge_into_global(p, gq, sv_a, si_a, idbase, g_s + wq * 128, g_id + wq * 128, m_l, K, lane);
         }
         // fresh rows for the next segment (another query block)
         m = 0;
@@ -1107,7 +1204,7 @@ static int score_tc_partition(int64_t n_query, int64_t n_cat, long long* tiles_p
 
 static int fixed_smem3(int hidden) {
   return (hidden / 64) * kQRows * 128 + 8 * kSlotRing3 * kSlotWords3 * 4 + 4 * 128 * 8 + kQRows * (kQCap2 + 1) * 8 +
-         kQRows * 12 + 128 + 8 + 1024 + 512;
+         4 * 128 * 12 /*global-list scratch*/ + kQRows * 12 + 128 + 8 + 1024 + 512;
 }
 // deep ring first (TMA latency x bandwidth), widest stage that allows it
 static ScoreCfg pick_cfg3(int hidden) {
@@ -1123,20 +1220,19 @@ static ScoreCfg pick_cfg3(int hidden) {
 bool score_tc_fits(int hidden) { return pick_cfg3(hidden).ns > 0; }
 
 size_t score_tc_workspace_bytes(int64_t n_query, int64_t n_cat, int hidden, int k) {
-  (void)hidden;
-  long long tpc;
-  int slots;
-  score_tc_partition(n_query, n_cat, &tpc, &slots);
-  return align_up((size_t)n_query * slots * k * 4, 256) + align_up((size_t)n_query * slots * k * 8, 256) +
-         align_up((size_t)n_query * 4, 256);
+  (void)n_cat; (void)hidden; (void)k;
+  return 2 * align_up((size_t)n_query * 4, 256);       // published thresholds + row locks
 }
 
-// partial-list slots a CTA never writes (a query block touched by fewer CTAs than `slots`) must read as empty
-__global__ void fill_parts(float* vals, long long* ids, long long n, int* thr, long long n_query) {
+// the rows' global lists start empty; thresholds at -inf; locks free
+__global__ void init_lists(float* vals, long long* ids, long long n, int* thr, int* locks, long long n_query) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     vals[i] = -INFINITY;
     ids[i] = kPadIdTc;
-    if (i < n_query) thr[i] = (int)0x807fffff;      // key of -inf
+    if (i < n_query) {
+      thr[i] = (int)0x807fffff;      // key of -inf
+      locks[i] = 0;
+    }
   }
 }
 
@@ -1169,22 +1265,20 @@ int score_topk_tc(const void* q, const void* cat, int64_t n_query, int64_t n_cat
   p.n_query = n_query; p.n_cat = n_cat; p.id_offset = id_offset; p.k = k; p.kblocks = hidden / 64;
   p.dbg = debug_env_int("TRG_TOPK_DBG", 0);
   const int grid = score_tc_partition(n_query, n_cat, &p.tiles_per_split, &p.n_splits);
-  p.part_vals = reinterpret_cast<float*>(ws);
-  p.part_ids = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) +
-                                            align_up((size_t)n_query * p.n_splits * k * 4, 256));
-  p.thr_shared = reinterpret_cast<int*>(reinterpret_cast<char*>(p.part_ids) +
-                                        align_up((size_t)n_query * p.n_splits * k * 8, 256));
-  const long long n_part = (long long)n_query * p.n_splits * k;
-  fill_parts<<<(unsigned)std::min<long long>(2048, (std::max<long long>(n_part, n_query) + 255) / 256), 256, 0, st>>>(
-      p.part_vals, p.part_ids, std::max<long long>(n_part, n_query), p.thr_shared, n_query);
+  p.thr_shared = reinterpret_cast<int*>(ws);
+  p.locks = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + align_up((size_t)n_query * 4, 256));
+  p.out_vals = vals_out;
+  p.out_ids = reinterpret_cast<long long*>(ids_out);
+  const long long n_out = std::max<long long>((long long)n_query * k, n_query);
+  init_lists<<<(unsigned)std::min<long long>(2048, (n_out + 255) / 256), 256, 0, st>>>(
+      p.out_vals, p.out_ids, (long long)n_query * k, p.thr_shared, p.locks, n_query);
   count_launch();
   rc = cfg.ns == kTileN2 ? launch_score3<kTileN2>(p, grid, cfg.smem, cfg.stages, st)
                          : launch_score3<kTileN2 / 2>(p, grid, cfg.smem, cfg.stages, st);
   if (rc) return rc;
   count_launch();
   TRG_LAUNCH_OK();
-  return trg_topk_merge(p.part_vals, (const int64_t*)p.part_ids, n_query, p.n_splits, k, k, vals_out,
-                        ids_out, st);
+  return TRG_OK;
 }
 
 }  // namespace tc
