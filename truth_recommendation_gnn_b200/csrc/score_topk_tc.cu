@@ -3,21 +3,24 @@
 // Replaces  scores = torch.mm(user_emb, known_post_emb.T); torch.topk(scores, min(K, n))
 // (inference.py:427-428) for batched queries against a large catalogue (BASELINE config 5:
 // 4096 x 50M, K = 100).  The [B, P] score matrix is never written: it only ever exists as
-// [128 x N] fp32 accumulator tiles in TMEM.
+// [128 x 128] fp32 accumulator tiles in TMEM.
 //
-// CTA = 128 queries (one TMEM lane each) x one contiguous catalogue split.
-//   warp 0   TMA: the query block once (all k-blocks resident), then catalogue tiles [N posts x H]
-//            through an mbarrier ring (SWIZZLE_128B, K-major)
-//   warp 1   one thread issues tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), accumulators
-//            double-buffered in TMEM columns [0, 256)
-//   warps 4+ selection: thread r owns query row r (= TMEM lane r); it reads its row of the accumulator
-//            tile with tcgen05.ld, rejects the whole tile with one max tree + one warp vote against the
-//            row's K-th best, pushes the few survivors to a per-thread queue in shared memory, and the
-//            warp merges full queues into the row's sorted top-K list (score desc, id asc; the stream is
-//            in ascending id order, so a tie with the K-th best never enters).  The lists live in TMEM
-//            columns [256, 512) of the row's own lane, which leaves shared memory to the catalogue ring.
-// Per-split lists go to the workspace and are merged by trg_topk_merge (also the multi-GPU merge).
+// One persistent CTA (16 warps) per SM; work = (catalogue chunk, 128-query block) items, chunk-major.
+//   warp 0      TMA: the item's query block (all k-blocks resident), then catalogue tiles [128 posts x H]
+//               through an mbarrier ring (SWIZZLE_128B, K-major)
+//   warp 1      one thread issues tcgen05.mma kind::f16 (bf16 in, fp32 accumulate), accumulators
+//               double-buffered in TMEM columns [0, 256)
+//   warps 4-11  SCAN: lane r of a quarter owns query row r (= TMEM lane r), two warps per quarter take 64
+//               columns each: tcgen05.ld, one max tree + one warp vote against the row's K-th best; a lane
+//               with a candidate copies its 64 scores into a hand-off slot
+//   warps 12-15 HELPER: exact test of the slot against the row's K-th best, candidate queue, bitonic sort +
+//               rank merge into the item's sorted list (score desc, id asc), which lives in TMEM columns
+//               [256, 512) of the row's own lane -- shared memory stays with the catalogue ring; at the end
+//               of an item, rank merge of the item's lists into the rows' GLOBAL lists (the result buffer)
+//               under one lock per row
 // Tensor-bound: 2*B*P*H flops against 2*P*H bytes of catalogue (AI = B = 4096 flop/B).
+// History and measurements of the earlier forms (v1: selection on the accumulator-reading warps; v2: scan /
+// helper split; v4: candidates filtered in registers -- slower at 50M posts, dropped): profiles/README.md.
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
@@ -34,7 +37,6 @@ constexpr int kQRows = 128;
 // the lists took in shared memory now hold catalogue ring stages (ablation in profiles/README.md: with
 // a 3 x 16 KB ring the TMA + MMA pipeline alone ran at 0.97 us per 128-post tile, 3.4x the MMA time).
 constexpr int kTmemColsTopk = 512;
-constexpr uint32_t kListScoreCol = 256, kListIdCol = 384;
 constexpr long long kPadIdTc = 0x7fffffffffffffffLL;
 
 struct ScoreTcParams {
@@ -45,10 +47,8 @@ struct ScoreTcParams {
   int k, n_splits, kblocks;   // kblocks = H / 64
   int dbg;                    // ablation switches, TRG_DEBUG builds only (TRG_TOPK_DBG): 1 = no selection, 2 = no tcgen05.ld either, 4 = no MMA
   int* thr_shared;            // [B] ordered-int keys of the best published K-th score per query row
-  float* part_vals;           // [B][n_splits][k]   (v1 / v2 kernels: per-split lists, merged by trg_topk_merge)
-  long long* part_ids;        // [B][n_splits][k]
-  int* locks;                 // [B] v3: one lock per query row's global list
-  float* out_vals;            // [B][k] v3: the rows' global top-K lists (= the result), merged into by every item
+  int* locks;                 // [B] one lock per query row's global list
+  float* out_vals;            // [B][k] the rows' global top-K lists (= the result), merged into by every item
   long long* out_ids;         // [B][k]
 };
 
@@ -65,9 +65,6 @@ __device__ __forceinline__ int float_key(float f) {
   return i ^ ((i >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
-__global__ void fill_int(int* p, long long n, int v) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
-}
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
@@ -161,456 +158,14 @@ __device__ __forceinline__ int warp_merge_row(uint32_t lv_a, uint32_t li_a, uint
   return min(K, m_l + n_c);
 }
 
-// ---- scan / helper split (v2) ------------------------------------------------------------------------
-// Cycle accounting of the kernel above (profiles/README.md, r1_v15): a selection warp spends 1 780 cycles
-// in every tile that holds a candidate (12 % of the tiles) and 9 400 in every queue merge, and because
-// the accumulator ring is two tiles deep the other three warps wait for it -- ~40 % of the tile time.
-// Here the warps that read the accumulators never leave the fast path:
-//   warps 4-7  SCAN: tcgen05.ld of the row, max tree, one vote.  A lane whose row has a candidate copies
-//              its 128 scores (32 x STS.128) into a slot of its quarter's ring and moves on.
-//   warps 8-11 HELPER (same TMEM lane quarter as warp - 4): take slots in order, test the 128 scores
-//              cooperatively (4 per lane) against the row's exact K-th best, append survivors to the row's
-//              queue and merge full queues into the row's list in TMEM.  Only the helper touches queues
-//              and lists, so there are no locks; the scan warps filter with a snapshot that may be stale
-//              (conservative), the helper ranks exactly, in stream order (= ascending id).
-//
-// Tried and measured (config 5): the query block as a TMEM-resident A operand (QT = true: copied once with
-// tcgen05.st, MMAs issued as umma_ts) with 96-post tiles so that accumulators (2 x 96), lists (2 x 128) and Q
-// (64 columns) fit the 512 TMEM columns.  Exact (all top-k tests pass) but no faster than Q in shared memory
-// at the same tile width (89.6 vs 89.7 ms), and 96-post tiles cost 15 % against 128-post ones (74 - 78 ms):
-// the slow shared-memory stores of the hand-off (~30 cycles per STS.128) are NOT caused by the MMA's operand
-// reads.  The product therefore runs 128-post tiles with Q in shared memory; the QT path stays compiled for
-// kTileN2 = 96 builds.
-constexpr int kSlotRing = 8;                 // slots per quarter
+// ---- tile / queue geometry ---------------------------------------------------------------------------
+// Tried and measured (config 5, on the v2 form): the query block as a TMEM-resident A operand with 96-post
+// tiles so that accumulators (2 x 96), lists (2 x 128) and Q (64 columns) fit the 512 TMEM columns.  Exact, but
+// no faster than Q in shared memory at the same tile width (89.6 vs 89.7 ms), and 96-post tiles cost 15 %
+// against 128-post ones: the product runs 128-post tiles with Q in shared memory.
 constexpr int kTileN2 = 128;                 // posts per accumulator tile
-constexpr int kSlotWords = kTileN2 + 4;      // scores + header (lane, base index, valid columns), 16 B aligned
-constexpr int kQCap2 = 32;
-constexpr uint32_t kListScoreCol2 = 2 * kTileN2, kListIdCol2 = kListScoreCol2 + 128, kQCol2 = kListIdCol2 + 128;
-
-template <int NS, bool QT>
-__global__ void __launch_bounds__(384, 1)
-    score_topk_tc2_kernel(const __grid_constant__ ScoreTcParams p, int n_stages) {
-  constexpr int N = kTileN2;
-  constexpr int kSub = N / NS;
-  constexpr int kChains = 8;
-  constexpr int kQStride = kQCap2 + 1;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int q_bytes = p.kblocks * kQRows * 128;
-  const int stage_bytes = p.kblocks * NS * 128;
-  unsigned char* q_smem = smem;
-  unsigned char* ring = smem + q_bytes;
-  uint32_t* slots = reinterpret_cast<uint32_t*>(ring + (size_t)n_stages * stage_bytes);   // [4][kSlotRing][kSlotWords]
-  float* sv = reinterpret_cast<float*>(slots + 4 * kSlotRing * kSlotWords);              // merge scratch [4][128]
-  uint32_t* si = reinterpret_cast<uint32_t*>(sv + 4 * 128);
-  float* cq_s = reinterpret_cast<float*>(si + 4 * 128);                                  // [128][kQStride]
-  uint32_t* cq_i = reinterpret_cast<uint32_t*>(cq_s + kQRows * kQStride);
-  uint2* row_thr = reinterpret_cast<uint2*>(
-      (reinterpret_cast<uintptr_t>(cq_i + kQRows * kQStride) + 7) & ~static_cast<uintptr_t>(7));   // (K-th score, K-th id)
-  float* row_tg = reinterpret_cast<float*>(row_thr + kQRows);                            // threshold of the other splits
-  volatile int* ctl = reinterpret_cast<volatile int*>(row_tg + kQRows);                  // [4][4]: head, tail, done
-  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(ctl) + 16);
-  uint64_t* full = bars;          // [8]
-  uint64_t* empty = full + 8;     // [8]
-  uint64_t* q_full = empty + 8;   // [1]
-  uint64_t* tmem_full = q_full + 1;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;  // [2]
-  uint64_t* q_tmem = tmem_empty + 2;     // [1] Q copied into tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_tmem + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long q0 = (long long)blockIdx.x * kQRows;
-  const int split = blockIdx.y;
-  const long long n_tiles_total = (p.n_cat + N - 1) / N;
-  const long long tile0 = (long long)split * p.tiles_per_split;
-  const long long tile1 = min(tile0 + p.tiles_per_split, n_tiles_total);
-  const int n_tiles = tile1 > tile0 ? (int)(tile1 - tile0) : 0;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.q_map);
-    tma_prefetch_desc(&p.c_map);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
-    }
-    mbar_init(smem_u32(q_full), 1);
-    mbar_init(smem_u32(q_tmem), 128);
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(smem_u32(&tmem_full[a]), 1);
-      mbar_init(smem_u32(&tmem_empty[a]), 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemColsTopk);
-  if (threadIdx.x >= 128 && threadIdx.x < 256) {
-    const int r = threadIdx.x - 128;
-    row_thr[r] = make_uint2(0xff800000u, 0xffffffffu);   // (-inf, max id): "list not full"
-    row_tg[r] = -INFINITY;
-    if (r < 16) ctl[r] = 0;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(smem_u32(q_full), (uint32_t)q_bytes);
-      for (int kb = 0; kb < p.kblocks; ++kb)
-        tma_load_2d(smem_u32(q_smem + kb * kQRows * 128), &p.q_map, smem_u32(q_full), kb * 64, (int)q0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < n_tiles * kSub; ++t) {
-        mbar_wait_backoff(smem_u32(&empty[stage]), phase ^ 1);
-        const uint32_t fb = smem_u32(&full[stage]);
-        mbar_arrive_expect_tx(fb, (uint32_t)stage_bytes);
-        const int row = (int)(tile0 * N + (long long)t * NS);
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_load_2d(smem_u32(ring + (size_t)stage * stage_bytes + kb * NS * 128), &p.c_map, fb, kb * 64, row);
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtBF16, 0, 0, kQRows, NS);
-      if (QT) {
-        mbar_wait(smem_u32(q_tmem), 0);
-        tc_fence_after();
-      } else {
-        mbar_wait(smem_u32(q_full), 0);
-      }
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait_backoff(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
-        tc_fence_after();
-        for (int sub = 0; sub < kSub; ++sub) {
-          mbar_wait_backoff(smem_u32(&full[stage]), phase);
-          tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(acc * N + sub * NS);
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            const uint64_t qd = make_smem_desc_sw128(smem_u32(q_smem + kb * kQRows * 128), 0, 1024);
-            const uint64_t cd = make_smem_desc_sw128(smem_u32(ring + (size_t)stage * stage_bytes + kb * NS * 128), 0, 1024);
-            if (!(TRG_TOPK_DBG(p) & 4)) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (QT)     // Q from tensor memory: 64 bf16 of a k-block = 32 columns, 16 per MMA = 8 columns
-                  umma_ts<false>(d, tmem_base + kQCol2 + (uint32_t)(kb * 32 + k * 8), cd + (uint64_t)(2 * k), idesc,
-                                 (kb | k) ? 1u : 0u);
-                else
-                  umma_ss<false>(d, qd + (uint64_t)(2 * k), cd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-              }
-            }
-          }
-          umma_commit(smem_u32(&empty[stage]));
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(smem_u32(&tmem_full[acc]));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== SCAN: one query row per thread, fast path only =====================
-    const int wq = warp & 3;
-    const int r = wq * 32 + lane;
-    const bool row_ok = q0 + r < p.n_query;
-    const uint32_t thr_addr = smem_u32(row_thr + r);
-    const uint32_t slot_base = smem_u32(slots + wq * kSlotRing * kSlotWords);
-    volatile int* c_head = ctl + wq * 4 + 0;
-    volatile int* c_tail = ctl + wq * 4 + 1;
-    volatile int* c_done = ctl + wq * 4 + 2;
-    float thr_g = row_ok ? -INFINITY : INFINITY;   // rows past B (zero-filled by TMA) never produce candidates
-    if (QT) {
-      // query block: shared memory (SWIZZLE_128B, K-major) -> this thread's TMEM lane; the 32-bit words go over
-      // as they are (bf16 pair k, k+1 of the row = one A-operand column)
-      mbar_wait(smem_u32(q_full), 0);
-      const uint32_t qrow = smem_u32(q_smem) + (uint32_t)r * 128u;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        uint32_t w[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 x = lds128(qrow + (uint32_t)(kb * kQRows * 128) + ((((uint32_t)c) ^ ((uint32_t)r & 7u)) << 4));
-          w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
-        }
-        tmem_st_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + kQCol2 + (uint32_t)(kb * 32), w);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(q_tmem));
-    }
-    int head = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const bool prof = (TRG_TOPK_DBG(p) & 8) != 0;      // cycle accounting, printed by CTA (0,0)
-    long long c_wait = 0, c_ld = 0, c_fast = 0, c_ev = 0, n_ev = 0, tk = 0, c_e1 = 0, c_e2 = 0, c_e3 = 0;
-    for (int t = 0; t < n_tiles; ++t) {
-      if (prof) tk = clock64();
-      int tg_key = 0;
-      const bool refresh = (t & 15) == 0 && row_ok;
-      if (refresh) tg_key = __ldcg(p.thr_shared + q0 + r);
-      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
-      tc_fence_after();
-      if (prof) { const long long n = clock64(); c_wait += n - tk; tk = n; }
-      const long long p0 = (tile0 + t) * N;
-      const long long left = p.n_cat - p0;
-      const int nvalid = left < (long long)N ? (int)left : N;
-      const uint32_t base_idx = (uint32_t)(p0 - tile0 * N);
-      uint32_t v[N];
-      const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * N);
-      if (TRG_TOPK_DBG(p) & 2) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) v[j] = 0xff800000u;
-      } else {
-#pragma unroll
-        for (int c = 0; c < N / 32; ++c) tmem_ld_32x32(t_row + (uint32_t)(c * 32), v + c * 32);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty[acc]));      // scores are in registers: hand the buffer back
-      if (prof) { const long long n = clock64(); c_ld += n - tk; tk = n; }
-      if (refresh) {
-        thr_g = fmaxf(thr_g, key_float(tg_key));
-        row_tg[r] = thr_g;                           // the helper filters with it too
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (TRG_TOPK_DBG(p) & 1) {
-        if (v[0] == 0x12345678u) head = 1;
-        continue;
-      }
-      uint32_t snap_s, snap_i;
-      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(snap_s), "=r"(snap_i) : "r"(thr_addr) : "memory");
-      const float thr = __uint_as_float(snap_s);
-      float mx[kChains];
-#pragma unroll
-      for (int c = 0; c < kChains; ++c) mx[c] = __uint_as_float(v[c]);
-#pragma unroll
-      for (int j = kChains; j < N; ++j) mx[j & (kChains - 1)] = fmaxf(mx[j & (kChains - 1)], __uint_as_float(v[j]));
-      float mall = mx[0];
-#pragma unroll
-      for (int c = 1; c < kChains; ++c) mall = fmaxf(mall, mx[c]);
-      const bool cand = mall >= thr && mall >= thr_g;
-      const unsigned mask = __ballot_sync(0xffffffffu, cand);
-      if (prof) { const long long n = clock64(); c_fast += n - tk; tk = n; }
-      // every lane with a candidate hands its whole row of the tile to the helper; when more lanes have
-      // one than the ring has free slots (the first tiles: every list is still empty) they go in rounds
-      unsigned rem = mask;
-      while (rem) {
-        int space = 0;
-        if (lane == 0) {
-          while ((space = kSlotRing - (head - *c_tail)) <= 0) {
-          }
-        }
-        space = __shfl_sync(0xffffffffu, space, 0);
-        long long te = 0;
-        if (prof) { te = clock64(); c_e1 += te - tk; }
-        const bool pending = (rem >> lane) & 1u;
-        const int k = __popc(rem & ((1u << lane) - 1u));
-        const bool go = pending && k < space;
-        if (go) {
-          const uint32_t sa = slot_base + (uint32_t)(((head + k) & (kSlotRing - 1)) * kSlotWords * 4);
-#pragma unroll
-          for (int i = 0; i < N / 4; ++i) sts128(sa + (uint32_t)(i * 16), make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-          sts128(sa + (uint32_t)(N * 4), make_uint4((uint32_t)lane, base_idx, (uint32_t)nvalid, 0u));
-        }
-        __syncwarp();
-        if (prof) { const long long n = clock64(); c_e2 += n - te; te = n; }
-        head += min(__popc(rem), space);
-        if (lane == 0) {
-          if (!(TRG_TOPK_DBG(p) & 16)) __threadfence_block();
-          *c_head = head;
-        }
-        if (prof) { const long long n = clock64(); c_e3 += n - te; }
-        rem = __ballot_sync(0xffffffffu, pending && !go);
-      }
-      if (prof && mask) { c_ev += clock64() - tk; ++n_ev; }
-    }
-    if (prof && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
-      printf("scan warp %d: tiles %d | cycles/tile: wait %.0f ld %.0f fast %.0f hand-off %.0f | hot tiles %.3f/tile, %.0f cyc each "
-             "(ring space %.0f, copy %.0f, publish %.0f)\n",
-             warp, n_tiles, (double)c_wait / n_tiles, (double)c_ld / n_tiles, (double)c_fast / n_tiles,
-             (double)c_ev / n_tiles, (double)n_ev / n_tiles, n_ev ? (double)c_ev / n_ev : 0.0,
-             n_ev ? (double)c_e1 / n_ev : 0.0, n_ev ? (double)c_e2 / n_ev : 0.0, n_ev ? (double)c_e3 / n_ev : 0.0);
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      *c_done = 1;
-    }
-  } else if (warp >= 8) {
-    // ===================== HELPER: candidates -> queues -> lists (TMEM) =====================
-    const int wq = warp & 3;
-    const int K = p.k;
-    const uint32_t qs_base = smem_u32(cq_s), qi_base = smem_u32(cq_i);
-    const uint32_t sv_a = smem_u32(sv + wq * 128), si_a = smem_u32(si + wq * 128);
-    const uint32_t tl_s = tmem_base + ((uint32_t)(wq * 32) << 16) + kListScoreCol2;
-    const uint32_t tl_i = tmem_base + ((uint32_t)(wq * 32) << 16) + kListIdCol2;
-    const uint32_t slot_base = smem_u32(slots + wq * kSlotRing * kSlotWords);
-    volatile int* c_head = ctl + wq * 4 + 0;
-    volatile int* c_tail = ctl + wq * 4 + 1;
-    volatile int* c_done = ctl + wq * 4 + 2;
-    int cnt = 0;     // lane l: entries in the queue of row 32 wq + l
-    int m = 0;       // lane l: entries in the list of row 32 wq + l
-    // merge the last `n_c` (<= 32) queue entries of row L into its list (TMEM lane L, staged through scratch)
-    auto merge_row = [&](int L, int n_c, int q_off) {
-      const int row = wq * 32 + L;
-      const int m_l = __shfl_sync(0xffffffffu, m, L);
-#pragma unroll 1
-      for (int c = 0; c * 16 < m_l; ++c) {
-        uint32_t rs[16], ri[16];
-        tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
-        tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
-        tmem_ld_wait();
-        if (lane == L) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            sts128(sv_a + 4u * (uint32_t)(c * 16 + j), make_uint4(rs[j], rs[j + 1], rs[j + 2], rs[j + 3]));
-            sts128(si_a + 4u * (uint32_t)(c * 16 + j), make_uint4(ri[j], ri[j + 1], ri[j + 2], ri[j + 3]));
-          }
-        }
-      }
-      __syncwarp();
-      const uint32_t qrow = (uint32_t)(row * kQStride + q_off);
-      const int nm = warp_merge_row(sv_a, si_a, qs_base + 4u * qrow, qi_base + 4u * qrow, n_c, m_l, K, lane);
-#pragma unroll 1
-      for (int c = 0; c * 16 < nm; ++c) {
-        uint32_t rs[16], ri[16];
-        tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
-        tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
-        tmem_ld_wait();
-        if (lane == L) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const uint4 a4 = lds128(sv_a + 4u * (uint32_t)(c * 16 + j));
-            const uint4 b4 = lds128(si_a + 4u * (uint32_t)(c * 16 + j));
-            rs[j] = a4.x; rs[j + 1] = a4.y; rs[j + 2] = a4.z; rs[j + 3] = a4.w;
-            ri[j] = b4.x; ri[j + 1] = b4.y; ri[j + 2] = b4.z; ri[j + 3] = b4.w;
-          }
-        }
-        tmem_st_32x16(tl_s + (uint32_t)(c * 16), rs);
-        tmem_st_32x16(tl_i + (uint32_t)(c * 16), ri);
-      }
-      tmem_st_wait();
-      if (lane == L) {
-        m = nm;
-        if (nm == K) {
-          const uint32_t ts = lds32(sv_a + 4u * (uint32_t)(K - 1));
-          const uint32_t ti = lds32(si_a + 4u * (uint32_t)(K - 1));
-          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(smem_u32(row_thr + row)), "r"(ts), "r"(ti) : "memory");
-          if (q0 + row < p.n_query) atomicMax(p.thr_shared + q0 + row, float_key(__uint_as_float(ts)));
-        }
-      }
-      __syncwarp();
-    };
-    auto drain_row = [&](int L) {      // empty row L's queue, 32 candidates at a time
-      int c = __shfl_sync(0xffffffffu, cnt, L);
-      while (c > 0) {
-        const int n_c = min(c, 32);
-        merge_row(L, n_c, c - n_c);
-        c -= n_c;
-      }
-      if (lane == L) cnt = 0;
-    };
-    int tail = 0;
-    for (;;) {
-      int h = 0, dn = 0;
-      if (lane == 0) {
-        h = *c_head;
-        if (h == tail) {
-          dn = *c_done;
-          if (dn) h = *c_head;      // done is published after the last head
-        }
-      }
-      h = __shfl_sync(0xffffffffu, h, 0);
-      dn = __shfl_sync(0xffffffffu, dn, 0);
-      if (h == tail) {
-        if (dn) break;
-        __nanosleep(64);
-        continue;
-      }
-      __threadfence_block();
-      for (; tail != h; ++tail) {
-        const uint32_t sa = slot_base + (uint32_t)((tail & (kSlotRing - 1)) * kSlotWords * 4);
-        const uint4 hdr = lds128(sa + (uint32_t)(N * 4));
-        const int L = (int)hdr.x;
-        const uint32_t base_idx = hdr.y;
-        const int nvalid = (int)hdr.z;
-        const int row = wq * 32 + L;
-        const float tg = *reinterpret_cast<volatile float*>(row_tg + row);
-#pragma unroll 1
-        for (int i = 0; i < N / 32; ++i) {
-          // the row's exact K-th best (it may have moved in the previous sub-step's merge)
-          uint32_t ts, ti;
-          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ts), "=r"(ti) : "r"(smem_u32(row_thr + row)) : "memory");
-          const float thr = __uint_as_float(ts);
-          const int j = i * 32 + lane;
-          const float s = __uint_as_float(lds32(sa + (uint32_t)(j * 4)));
-          const uint32_t id = base_idx + (uint32_t)j;
-          const bool pass = j < nvalid && s >= tg && (s > thr || (s == thr && id < ti));
-          const unsigned pm = __ballot_sync(0xffffffffu, pass);
-          if (pm) {
-            const int n = __popc(pm);
-            int c = __shfl_sync(0xffffffffu, cnt, L);
-            if (c + n > kQCap2) {            // make room: merge what is queued (the threshold only gets tighter;
-              drain_row(L);                  // survivors of the stale test are re-ranked exactly by the merge)
-              c = 0;
-            }
-            if (pass) {
-              const int k = c + __popc(pm & ((1u << lane) - 1u));
-              sts32(qs_base + 4u * (uint32_t)(row * kQStride + k), __float_as_uint(s));
-              sts32(qi_base + 4u * (uint32_t)(row * kQStride + k), id);
-            }
-            __syncwarp();
-            if (lane == L) cnt = c + n;
-          }
-        }
-        if (__shfl_sync(0xffffffffu, cnt, L) > 16) drain_row(L);
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence_block();
-          *c_tail = tail + 1;
-        }
-      }
-    }
-    // merge what is left in the queues, then every thread writes its own row's list
-    {
-      unsigned need = __ballot_sync(0xffffffffu, cnt > 0);
-      while (need) {
-        const int L = __ffs(need) - 1;
-        need &= need - 1;
-        drain_row(L);
-      }
-    }
-    {
-      const int r = wq * 32 + lane;
-      const bool row_ok = q0 + r < p.n_query;
-      float* ov = p.part_vals + ((q0 + r) * p.n_splits + split) * K;
-      long long* oi = p.part_ids + ((q0 + r) * p.n_splits + split) * K;
-      const long long idbase = p.id_offset + tile0 * N;
-#pragma unroll 1
-      for (int c = 0; c * 16 < K; ++c) {
-        uint32_t rs[16], ri[16];
-        tmem_ld_32x16(tl_s + (uint32_t)(c * 16), rs);
-        tmem_ld_32x16(tl_i + (uint32_t)(c * 16), ri);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int i = c * 16 + j;
-            if (i < K) {
-              ov[i] = i < m ? __uint_as_float(rs[j]) : -INFINITY;
-              oi[i] = i < m ? idbase + (long long)ri[j] : kPadIdTc;
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemColsTopk);
-}
+constexpr int kQCap2 = 32;                   // candidates a row queues before they are merged into its list
+constexpr uint32_t kListScoreCol2 = 2 * kTileN2, kListIdCol2 = kListScoreCol2 + 128;
 
 // ---- v3: two scan warps per TMEM lane quarter, work-balanced over every SM ---------------------------
 // Measured on v2 (profiles/README.md "K5 v2"): per 128-post tile a scan warp spends 430-500 cycles in the
