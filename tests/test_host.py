@@ -184,3 +184,44 @@ def test_negative_share_capacity_covers_randint_modulo_bias():
     # the observed overflow: 100 132 949 selected at config 4
     sh.num_posts, sh.n_pos_global, sh.world, sh.cp = 50_000_000, 800_000_000, 8, 6_250_000
     assert sh.neg_capacity() > 100_132_949
+
+
+def test_bench_reference_arm_line_contract():
+    """``bench.py --impl reference`` (the driver runs it next to the GPU arm): one JSON line on stdout with the
+    contract's keys, the SAME ``config`` object the GPU arm prints for that workload, and a ``cpu_baseline``
+    describing the run.  Runs the tiny workload on the CPU oracle (no GPU involved)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "tiny", "--steps", "2",
+                        "--warmup", "1", "--no-extras"], capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["higher_is_better"] is True
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.config_of("tiny", bench.WORKLOADS["tiny"])      # identical in both arms
+    assert d["value"] > 0 and d["steps"] == 2
+
+
+def test_bench_refuses_to_run_the_product_without_a_gpu():
+    """The GPU arm has no CPU fallback: without a CUDA device it stops with a message, it does not time the oracle."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--workload", "tiny", "--steps", "1"], capture_output=True,
+                       text=True, cwd=root, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
