@@ -34,5 +34,10 @@ PARITY PIN STATUS
   ``count.clamp(min=1)``; ``out = lin_l(mean) + lin_r(x_dst)``) and is anchored on the
   reference's call sites and on dense-adjacency math (``tests/test_oracle.py``), plus the
   committed fixtures under ``tests/golden/`` produced by ``tests/golden/make_golden.py``.
+* everything AROUND that operator is pinned to the reference's own text:
+  ``tests/golden/make_golden_ref.py`` extracts ``WeightedRGCN``, ``train()``, ``evaluate()`` and
+  ``build_edge_index_safe`` from ``/root/reference/train_gnn.py`` by name (``ast``) and executes them
+  unmodified with ``SAGEConv`` bound to ``sage.SAGEConvOracle``; the outputs are the committed
+  ``tests/golden/ref_exec_*.pt`` fixtures that ``tests/test_oracle.py`` holds this package to.
 """
 from . import csr, sage, topk  # noqa: F401  (oracle.evaluate needs sklearn: imported on demand)
