@@ -764,8 +764,10 @@ static int fixed_smem3(int hidden) {
 // deep ring first (TMA latency x bandwidth), widest stage that allows it
 static ScoreCfg pick_cfg3(int hidden) {
   const int fixed = fixed_smem3(hidden);
+  const int force_ns = debug_env_int("TRG_TOPK_NS", 0);      // TRG_DEBUG builds only: stage width A/B
   for (int min_stages : {4, 2})
     for (int ns : {kTileN2, kTileN2 / 2}) {
+      if (force_ns && ns != force_ns) continue;
       const int stage = (hidden / 64) * ns * 128;
       const int stages = std::min(8, (kSmemLimit - fixed) / stage);
       if (stages >= min_stages) return {ns, stages, fixed + stages * stage};
