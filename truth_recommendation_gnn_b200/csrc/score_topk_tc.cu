@@ -215,9 +215,10 @@ __device__ __forceinline__ bool next_segment(const ScoreTcParams& p, long long n
 // inserted >= K candidates per row again (37 chunks x ~150 insertions per row at config 5) and the candidate
 // work was a fixed ~21 ms whatever the catalogue size (65.6 ms at 50M posts, 29.9 ms at 10M: r2 same-box A/B);
 // with the global K-th best the later items insert K x chunk / seen.  gs / gid: scratch for 128 scores / ids.
-__device__ __forceinline__ void merge_into_global(const ScoreTcParams& p, long long gq, uint32_t lv_a, uint32_t li_a,
-                                                  long long idbase, float* gs, long long* gid, int m_l, int K,
-                                                  int lane) {
+// Returns the K-th best score of the merged global list (-inf while it holds fewer than K entries).
+__device__ __forceinline__ float merge_into_global(const ScoreTcParams& p, long long gq, uint32_t lv_a, uint32_t li_a,
+                                                   long long idbase, float* gs, long long* gid, int m_l, int K,
+                                                   int lane) {
   if (lane == 0) {
     while (atomicCAS(p.locks + gq, 0, 1) != 0) __nanosleep(100);
     __threadfence();
@@ -277,22 +278,31 @@ __device__ __forceinline__ void merge_into_global(const ScoreTcParams& p, long l
     }
   }
   __syncwarp();
+  int kth_key = (int)0x80000000;          // below every float key
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     if (lane + 32 * t < mg && pos_g[t] < K) {
       gv[pos_g[t]] = s_g[t];
       gi[pos_g[t]] = id_g[t];
-      if (pos_g[t] == K - 1) atomicMax(p.thr_shared + gq, float_key(s_g[t]));
+      if (pos_g[t] == K - 1) {
+        kth_key = float_key(s_g[t]);
+        atomicMax(p.thr_shared + gq, kth_key);
+      }
     }
     if (pos_l[t] < K) {
       gv[pos_l[t]] = s_l[t];
       gi[pos_l[t]] = id_l[t];
-      if (pos_l[t] == K - 1) atomicMax(p.thr_shared + gq, float_key(s_l[t]));
+      if (pos_l[t] == K - 1) {
+        kth_key = float_key(s_l[t]);
+        atomicMax(p.thr_shared + gq, kth_key);
+      }
     }
   }
   __threadfence();
   __syncwarp();
   if (lane == 0) atomicExch(p.locks + gq, 0);
+  kth_key = __reduce_max_sync(0xffffffffu, kth_key);
+  return kth_key == (int)0x80000000 ? -INFINITY : key_float(kth_key);
 }
 
 template <int NS>
@@ -532,6 +542,7 @@ __global__ void __launch_bounds__(512, 1)
     const uint32_t tl_s = tmem_base + ((uint32_t)(wq * 32) << 16) + kListScoreCol2;
     const uint32_t tl_i = tmem_base + ((uint32_t)(wq * 32) << 16) + kListIdCol2;
     long long q0 = 0;
+    long long idbase = 0;   // global id of the current item's first post
     int cnt = 0;     // lane l: entries in the queue of row 32 wq + l
     int m = 0;       // lane l: entries in the list of row 32 wq + l
     // merge the last `n_c` (<= 32) queue entries of row L into its list (TMEM lane L, staged through scratch)
@@ -555,6 +566,23 @@ __global__ void __launch_bounds__(512, 1)
       __syncwarp();
       const uint32_t qrow = (uint32_t)(row * kQStride + q_off);
       const int nm = warp_merge_row(sv_a, si_a, qs_base + 4u * qrow, qi_base + 4u * qrow, n_c, m_l, K, lane);
+      if (nm == K && q0 + row < p.n_query) {
+        // FLUSH: a list that has filled up goes straight into the row's global list (from the scratch the merge
+        // left it in: no TMEM write-back) and the row restarts empty, filtered by the K-th best of EVERYTHING
+        // every CTA has flushed so far.  The CTAs that work on the same query rows at the same time (4.6 per
+        // query block at config 5) thereby share one threshold while they are all still cold, instead of each
+        // paying the K ln(n / K) insertions of a private list.  The id of the global K-th best may belong to
+        // another chunk, so the row's exact test keeps every candidate that TIES with it (id = max): the
+        // global merge ranks them exactly.
+        const float kth = merge_into_global(p, q0 + row, sv_a, si_a, idbase, g_s + wq * 128, g_id + wq * 128, nm, K, lane);
+        if (lane == L) {
+          m = 0;
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(smem_u32(row_thr + row)), "r"(__float_as_uint(kth)),
+                       "r"(0xffffffffu) : "memory");
+        }
+        __syncwarp();
+        return;
+      }
 #pragma unroll 1
       for (int c = 0; c * 16 < nm; ++c) {
         uint32_t rs[16], ri[16];
@@ -638,6 +666,7 @@ __global__ void __launch_bounds__(512, 1)
     Seg3 sg;
     while (next_segment(p, n_tiles_total, n_qb, item, sg)) {
       q0 = sg.qb * kQRows;
+      idbase = p.id_offset + sg.tile0 * N;
       for (;;) {
         // poll the two rings of this quarter (SCAN A: ring wq, SCAN B: ring 4 + wq)
         int h[2] = {0, 0}, dn[2] = {0, 0};
@@ -688,7 +717,6 @@ __global__ void __launch_bounds__(512, 1)
       {
         // the item is done: merge every row's list into the row's global list (the result)
         const int r = wq * 32 + lane;
-        const long long idbase = p.id_offset + sg.tile0 * N;
         for (int L = 0; L < 32; ++L) {
           const int m_l = __shfl_sync(0xffffffffu, m, L);
           const long long gq = q0 + wq * 32 + L;
